@@ -1,0 +1,236 @@
+// Shared device/host helpers for the b200u kernels (sm_100a only).
+//
+// Everything in csrc/ is written for one target: -gencode arch=compute_100a,code=sm_100a.
+// The library never allocates or frees device memory and never synchronises; every entry
+// point enqueues on the caller's stream so the whole step can be captured in a CUDA graph.
+#pragma once
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+// ---------------------------------------------------------------------------------------
+// Error plumbing: C-ABI returns 0 / negative code, message via b200u_last_error_string().
+// ---------------------------------------------------------------------------------------
+namespace b200u {
+
+void set_error(const char* fmt, ...);
+
+#define B200U_OK 0
+#define B200U_ERR_ARG -1
+#define B200U_ERR_CUDA -2
+#define B200U_ERR_UNSUPPORTED -3
+
+#define B200U_CHECK_ARG(cond, ...)                                     \
+    do {                                                               \
+        if (!(cond)) {                                                 \
+            ::b200u::set_error(__VA_ARGS__);                           \
+            return B200U_ERR_ARG;                                      \
+        }                                                              \
+    } while (0)
+
+#define B200U_CHECK_LAUNCH(name)                                                        \
+    do {                                                                                \
+        cudaError_t _e = cudaGetLastError();                                            \
+        if (_e != cudaSuccess) {                                                        \
+            ::b200u::set_error("%s: launch failed: %s", name, cudaGetErrorString(_e));  \
+            return B200U_ERR_CUDA;                                                      \
+        }                                                                               \
+    } while (0)
+
+#define B200U_CHECK_CUDA(expr)                                                               \
+    do {                                                                                     \
+        cudaError_t _e = (expr);                                                             \
+        if (_e != cudaSuccess) {                                                             \
+            ::b200u::set_error("%s failed: %s", #expr, cudaGetErrorString(_e));              \
+            return B200U_ERR_CUDA;                                                           \
+        }                                                                                    \
+    } while (0)
+
+int num_sms();  // cached cudaDevAttrMultiProcessorCount of the current device
+
+typedef __nv_bfloat16 bf16;
+typedef __nv_bfloat162 bf162;
+
+// ---------------------------------------------------------------------------------------
+// Counter-based dropout RNG.
+// One call yields 32 bits = two 16-bit uniform samples for an element PAIR; an element is
+// kept when its sample >= thresh16 (thresh16 = round(p * 65536)). The mapping depends only on
+// (seed, stream, pair index), so forward and backward kernels regenerate identical masks
+// without storing them. `seed` lives in device memory so a captured CUDA graph sees a fresh
+// value on every replay.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t rng_mix(uint32_t x) {
+    x ^= x >> 16;
+    x *= 0x7feb352dU;
+    x ^= x >> 15;
+    x *= 0x846ca68bU;
+    x ^= x >> 16;
+    return x;
+}
+__device__ __forceinline__ uint32_t rng_pair(uint64_t seed, uint32_t stream, uint32_t pair_idx) {
+    uint32_t h = rng_mix(pair_idx ^ (uint32_t)seed ^ (stream * 0x9E3779B9U));
+    return rng_mix(h + (uint32_t)(seed >> 32) + stream * 0x85EBCA6BU);
+}
+struct DropoutCfg {
+    const unsigned long long* seed_ptr;  // device pointer, may be null when thresh16 == 0
+    uint32_t stream;                     // distinct per (layer, site)
+    uint32_t thresh16;                   // 0 => dropout disabled
+    float scale;                         // 1 / (1 - p)
+};
+__device__ __forceinline__ uint64_t load_seed(const DropoutCfg& d) {
+    return d.thresh16 ? *d.seed_ptr : 0ull;
+}
+
+// ---------------------------------------------------------------------------------------
+// Small math helpers (reference: model/layer.py:31-37 exact erf GELU).
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ float gelu_erf(float x) {
+    return x * 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+}
+__device__ __forceinline__ float gelu_erf_grad(float x) {
+    float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+    float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
+    return cdf + x * pdf;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+    bf162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float2 unpack_bf16(uint32_t u) {
+    bf162 v = *reinterpret_cast<bf162*>(&u);
+    return __bfloat1622float2(v);
+}
+
+// ---------------------------------------------------------------------------------------
+// PTX wrappers: mbarrier, TMA, tcgen05 / TMEM.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return done != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+
+// 2-D tiled TMA load: box lands at `dst` (swizzled as the tensor map says), completion is
+// signalled as transaction bytes on `bar`. c0 = innermost (contiguous) coordinate.
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tmap, uint64_t* bar,
+                                            int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes "
+        "[%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tmap) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() {
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem) {  // whole warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(dst_smem)),
+                 "n"(NCOLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {  // whole warp
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS)
+                 : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], bf16 inputs, fp32 accumulate. One thread issues.
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                          uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// Arrive on `bar` once every tcgen05.mma previously issued by this thread has completed.
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                     smem_u32(bar))
+                 : "memory");
+}
+// TMEM -> registers: this thread's lane (row), 32 consecutive fp32 columns.
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+          "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+          "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),
+          "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]),
+          "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Vector fp32 reduction into global memory (split-K wgrad accumulation).
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c),
+                 "f"(d)
+                 : "memory");
+}
+
+}  // namespace b200u

@@ -1,0 +1,438 @@
+// HBM/L2-bound row kernels of the UNITER path (sm_100a): LayerNorm fwd/bwd with fused
+// dropout-mask and bias-grad, column sums, fp32->bf16 casts, the bit-exact gather_index
+// concat (K1) and its backward. One warp owns one row; every access is a 16-byte vector.
+//
+// Reference arithmetic:
+//   LayerNorm  : apex FusedLayerNorm(H, eps=1e-12) == (x-mean)/sqrt(var+eps)*gamma+beta with
+//                biased variance (model/model.py:229,252,253,258; model/layer.py:108,149)
+//   gather     : torch.gather(torch.cat([txt_emb, img_emb], 1), 1, gather_index) (model/model.py:330-333)
+#include "../../include/b200u.h"
+#include "common.cuh"
+
+namespace b200u {
+
+constexpr int LN_MAXV = 4;  // vectors (of 8 elements) per lane -> H <= 1024
+
+template <typename T>
+__device__ __forceinline__ void load8(const T* p, float (&f)[8]);
+template <>
+__device__ __forceinline__ void load8<bf16>(const bf16* p, float (&f)[8]) {
+    uint4 u = *reinterpret_cast<const uint4*>(p);
+    float2 t;
+    t = unpack_bf16(u.x); f[0] = t.x; f[1] = t.y;
+    t = unpack_bf16(u.y); f[2] = t.x; f[3] = t.y;
+    t = unpack_bf16(u.z); f[4] = t.x; f[5] = t.y;
+    t = unpack_bf16(u.w); f[6] = t.x; f[7] = t.y;
+}
+template <>
+__device__ __forceinline__ void load8<float>(const float* p, float (&f)[8]) {
+    float4 a = *reinterpret_cast<const float4*>(p);
+    float4 b = *reinterpret_cast<const float4*>(p + 4);
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
+    f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+template <typename T>
+__device__ __forceinline__ void store8(T* p, const float (&f)[8]);
+template <>
+__device__ __forceinline__ void store8<bf16>(bf16* p, const float (&f)[8]) {
+    uint4 o;
+    o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]);
+    o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
+    *reinterpret_cast<uint4*>(p) = o;
+}
+template <>
+__device__ __forceinline__ void store8<float>(float* p, const float (&f)[8]) {
+    *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(f[4], f[5], f[6], f[7]);
+}
+
+// Row statistics over values held in registers (two-pass: mean, then centred variance).
+__device__ __forceinline__ void row_stats(const float (&x)[LN_MAXV][8], int nv, int lane, int H,
+                                          float eps, float& mean, float& rstd) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i)
+        if (lane + 32 * i < nv)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s += x[i][j];
+    mean = warp_sum(s) / (float)H;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i)
+        if (lane + 32 * i < nv)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float d = x[i][j] - mean;
+                q += d * d;
+            }
+    rstd = rsqrtf(warp_sum(q) / (float)H + eps);
+}
+
+// ---------------------------------------------------------------------------------------
+// LayerNorm forward: y = (x - mean) * rstd * gamma + beta ; optional dropout on y.
+// ---------------------------------------------------------------------------------------
+template <typename TIn, typename TOut>
+__global__ void __launch_bounds__(256)
+layernorm_fwd_kernel(const TIn* __restrict__ x, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, TOut* __restrict__ y, float* __restrict__ mean_out,
+                     float* __restrict__ rstd_out, int M, int H, float eps, DropoutCfg drop) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= M) return;
+    const int nv = H >> 3;
+    float v[LN_MAXV][8];
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i)
+        if (lane + 32 * i < nv) load8(x + (size_t)row * H + (lane + 32 * i) * 8, v[i]);
+    float mean, rstd;
+    row_stats(v, nv, lane, H, eps, mean, rstd);
+    if (lane == 0) {
+        if (mean_out) mean_out[row] = mean;
+        if (rstd_out) rstd_out[row] = rstd;
+    }
+    const uint64_t seed = load_seed(drop);
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+        const int vi = lane + 32 * i;
+        if (vi < nv) {
+            float g[8], b[8], o[8];
+            load8(gamma + vi * 8, g);
+            load8(beta + vi * 8, b);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rstd * g[j] + b[j];
+            if (drop.thresh16) {
+                const uint32_t pbase = (uint32_t)(((size_t)row * H + vi * 8) >> 1);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    uint32_t h = rng_pair(seed, drop.stream, pbase + j);
+                    o[2 * j] = ((h & 0xffffu) >= drop.thresh16) ? o[2 * j] * drop.scale : 0.f;
+                    o[2 * j + 1] = ((h >> 16) >= drop.thresh16) ? o[2 * j + 1] * drop.scale : 0.f;
+                }
+            }
+            store8(y + (size_t)row * H + vi * 8, o);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// LayerNorm backward for y = LN(x):
+//   dx = rstd * (g*dy - mean_H(g*dy) - xhat * mean_H(g*dy*xhat))
+//   dgamma += sum_rows dy*xhat ; dbeta += sum_rows dy
+// Fused extras for the BertSelfOutput / BertOutput pattern x = dropout(dense) + residual
+// (model/layer.py:111-115,152-156): dz = dropout_mask(dx) (the dense output's grad, bf16) and
+// dbias += sum_rows dz. dx itself is the residual-branch grad.
+// ---------------------------------------------------------------------------------------
+template <typename TX>
+__global__ void __launch_bounds__(256)
+layernorm_bwd_kernel(const bf16* __restrict__ dy, const TX* __restrict__ x,
+                     const float* __restrict__ mean, const float* __restrict__ rstd,
+                     const float* __restrict__ gamma, bf16* __restrict__ dx, bf16* __restrict__ dz,
+                     float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias,
+                     int M, int H, DropoutCfg drop) {
+    extern __shared__ float red[];  // [warps][H]
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int nwarps = blockDim.x >> 5;
+    const int nv = H >> 3;
+    const uint64_t seed = load_seed(drop);
+
+    float ag[LN_MAXV][8], ab[LN_MAXV][8], az[LN_MAXV][8];
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ag[i][j] = ab[i][j] = az[i][j] = 0.f;
+
+    for (int row = blockIdx.x * nwarps + warp; row < M; row += gridDim.x * nwarps) {
+        const float mu = mean[row], rs = rstd[row];
+        float xh[LN_MAXV][8], gd[LN_MAXV][8];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < LN_MAXV; ++i) {
+            const int vi = lane + 32 * i;
+            if (vi < nv) {
+                float d[8], g[8];
+                load8(x + (size_t)row * H + vi * 8, xh[i]);
+                load8(dy + (size_t)row * H + vi * 8, d);
+                load8(gamma + vi * 8, g);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    xh[i][j] = (xh[i][j] - mu) * rs;
+                    ag[i][j] += d[j] * xh[i][j];
+                    ab[i][j] += d[j];
+                    gd[i][j] = d[j] * g[j];
+                    s1 += gd[i][j];
+                    s2 += gd[i][j] * xh[i][j];
+                }
+            }
+        }
+        s1 = warp_sum(s1) / (float)H;
+        s2 = warp_sum(s2) / (float)H;
+#pragma unroll
+        for (int i = 0; i < LN_MAXV; ++i) {
+            const int vi = lane + 32 * i;
+            if (vi < nv) {
+                float o[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o[j] = rs * (gd[i][j] - s1 - xh[i][j] * s2);
+                if (dx) store8(dx + (size_t)row * H + vi * 8, o);
+                if (dz) {
+                    if (drop.thresh16) {
+                        const uint32_t pbase = (uint32_t)(((size_t)row * H + vi * 8) >> 1);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            uint32_t h = rng_pair(seed, drop.stream, pbase + j);
+                            o[2 * j] = ((h & 0xffffu) >= drop.thresh16) ? o[2 * j] * drop.scale : 0.f;
+                            o[2 * j + 1] = ((h >> 16) >= drop.thresh16) ? o[2 * j + 1] * drop.scale : 0.f;
+                        }
+                    }
+                    store8(dz + (size_t)row * H + vi * 8, o);
+                }
+                if (dbias) {
+                    // column sums of the bf16-rounded dz: exactly what the wgrad GEMM consumes
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) az[i][j] += __bfloat162float(__float2bfloat16(o[j]));
+                }
+            }
+        }
+    }
+
+    // cross-warp reduction of the three column accumulators, one at a time through smem
+    for (int which = 0; which < 3; ++which) {
+        float* dst = which == 0 ? dgamma : (which == 1 ? dbeta : dbias);
+        if (!dst) continue;  // uniform
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < LN_MAXV; ++i) {
+            const int vi = lane + 32 * i;
+            if (vi < nv)
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    red[warp * H + vi * 8 + j] = which == 0 ? ag[i][j] : (which == 1 ? ab[i][j] : az[i][j]);
+        }
+        __syncthreads();
+        for (int c = threadIdx.x; c < H; c += blockDim.x) {
+            float s = 0.f;
+            for (int w = 0; w < nwarps; ++w) s += red[w * H + c];
+            atomicAdd(dst + c, s);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// out[n] += sum_m x[m, n]   (bias gradients of the GEMMs whose dY comes from another GEMM /
+// the attention backward). Block = 8 warps x 256 columns; rows strided over blockIdx.y.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+colsum_kernel(const bf16* __restrict__ x, int ldx, float* __restrict__ out, int M, int N) {
+    __shared__ float red[8][256];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int col = blockIdx.x * 256 + lane * 8;
+    float a[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] = 0.f;
+    if (col < N) {
+        for (int row = blockIdx.y * 8 + warp; row < M; row += gridDim.y * 8) {
+            float v[8];
+            load8(x + (size_t)row * ldx + col, v);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a[j] += v[j];
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[warp][lane * 8 + j] = a[j];
+    __syncthreads();
+    const int c = blockIdx.x * 256 + threadIdx.x;
+    if (c < N) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+        atomicAdd(out + c, s);
+    }
+}
+
+// fp32 -> bf16 cast (n multiple of 8), grid-stride.
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ y, size_t nvec) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nvec;
+         i += (size_t)gridDim.x * blockDim.x) {
+        float f[8];
+        load8(x + i * 8, f);
+        store8(y + i * 8, f);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// K1 gather: out[b, j, :] = (idx < T ? txt[b, idx] : img[b, idx - T]),  idx = gather_index[b, j]
+// Pure 16-byte row copies -> bit-exact with torch.gather on the concatenation, padded
+// positions included. Index is read once per row, never expanded.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+gather_rows_kernel(const bf16* __restrict__ txt, const bf16* __restrict__ img,
+                   const long long* __restrict__ gidx, bf16* __restrict__ out, int B, int T, int R,
+                   int L, int H) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= B * L) return;
+    const int b = row / L;
+    const long long idx = gidx[row];
+    const bf16* src = (idx < T) ? txt + ((size_t)b * T + idx) * H : img + ((size_t)b * R + (idx - T)) * H;
+    const uint4* s4 = reinterpret_cast<const uint4*>(src);
+    uint4* d4 = reinterpret_cast<uint4*>(out + (size_t)row * H);
+    for (int v = lane; v < (H >> 3); v += 32) d4[v] = s4[v];
+}
+
+// Backward of the gather = scatter-add; done as a deterministic inverse scan: the warp that owns
+// source row s of sample b sums every dout[b, j] with gather_index[b, j] == s (fp32), so duplicate
+// indices (the identity tail of get_gather_index) need no atomics.
+__global__ void __launch_bounds__(256)
+gather_rows_bwd_kernel(const bf16* __restrict__ dout, const long long* __restrict__ gidx,
+                       bf16* __restrict__ dtxt, bf16* __restrict__ dimg, int B, int T, int R, int L,
+                       int H) {
+    const int lane = threadIdx.x & 31;
+    const int srow = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int S = T + R;
+    if (srow >= B * S) return;
+    const int b = srow / S, s = srow - b * S;
+    const int nv = H >> 3;
+    float acc[LN_MAXV][8];
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    for (int j0 = 0; j0 < L; j0 += 32) {
+        const int j = j0 + lane;
+        const bool hit = (j < L) && (gidx[(size_t)b * L + j] == (long long)s);
+        unsigned m = __ballot_sync(0xffffffffu, hit);
+        while (m) {
+            const int jj = j0 + __ffs(m) - 1;
+            m &= m - 1;
+#pragma unroll
+            for (int i = 0; i < LN_MAXV; ++i) {
+                const int vi = lane + 32 * i;
+                if (vi < nv) {
+                    float d[8];
+                    load8(dout + ((size_t)b * L + jj) * H + vi * 8, d);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) acc[i][k] += d[k];
+                }
+            }
+        }
+    }
+    bf16* dst = (s < T) ? dtxt + ((size_t)b * T + s) * H : dimg + ((size_t)b * R + (s - T)) * H;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+        const int vi = lane + 32 * i;
+        if (vi < nv) store8(dst + vi * 8, acc[i]);
+    }
+}
+
+static DropoutCfg make_drop(const b200u_dropout_t& d) {
+    DropoutCfg c;
+    c.seed_ptr = d.seed_ptr;
+    c.stream = d.stream;
+    c.thresh16 = (uint32_t)(d.p * 65536.0f + 0.5f);
+    c.scale = 1.0f / (1.0f - d.p);
+    return c;
+}
+
+}  // namespace b200u
+
+using namespace b200u;
+
+#define CHECK_H(H) \
+    B200U_CHECK_ARG((H) > 0 && (H) % 8 == 0 && (H) <= 8 * 32 * LN_MAXV, "hidden size %d unsupported (need H%%8==0, H<=1024)", (H))
+
+extern "C" int b200u_layernorm_fwd(const void* x, int x_dtype, const float* gamma, const float* beta,
+                                   void* y, int y_dtype, float* mean, float* rstd, int M, int H,
+                                   float eps, const b200u_dropout_t* drop, b200u_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    CHECK_H(H);
+    B200U_CHECK_ARG(M >= 0 && x && gamma && beta && y, "layernorm_fwd: null pointer");
+    if (M == 0) return B200U_OK;
+    b200u_dropout_t nodrop = {nullptr, 0, 0.f};
+    DropoutCfg dc = make_drop(drop ? *drop : nodrop);
+    B200U_CHECK_ARG(dc.thresh16 == 0 || dc.seed_ptr, "layernorm_fwd: dropout needs seed_ptr");
+    const int grid = (M + 7) / 8;
+    if (x_dtype == B200U_BF16 && y_dtype == B200U_BF16)
+        layernorm_fwd_kernel<bf16, bf16><<<grid, 256, 0, stream>>>((const bf16*)x, gamma, beta, (bf16*)y, mean, rstd, M, H, eps, dc);
+    else if (x_dtype == B200U_F32 && y_dtype == B200U_BF16)
+        layernorm_fwd_kernel<float, bf16><<<grid, 256, 0, stream>>>((const float*)x, gamma, beta, (bf16*)y, mean, rstd, M, H, eps, dc);
+    else if (x_dtype == B200U_F32 && y_dtype == B200U_F32)
+        layernorm_fwd_kernel<float, float><<<grid, 256, 0, stream>>>((const float*)x, gamma, beta, (float*)y, mean, rstd, M, H, eps, dc);
+    else
+        B200U_CHECK_ARG(false, "layernorm_fwd: unsupported dtype combination %d -> %d", x_dtype, y_dtype);
+    B200U_CHECK_LAUNCH("layernorm_fwd");
+    return B200U_OK;
+}
+
+extern "C" int b200u_layernorm_bwd(const void* dy, const void* x, int x_dtype, const float* mean,
+                                   const float* rstd, const float* gamma, void* dx, void* dz,
+                                   float* dgamma, float* dbeta, float* dbias, int M, int H,
+                                   const b200u_dropout_t* drop, b200u_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    CHECK_H(H);
+    B200U_CHECK_ARG(dy && x && mean && rstd && gamma, "layernorm_bwd: null pointer");
+    if (M == 0) return B200U_OK;
+    b200u_dropout_t nodrop = {nullptr, 0, 0.f};
+    DropoutCfg dc = make_drop(drop ? *drop : nodrop);
+    B200U_CHECK_ARG(dc.thresh16 == 0 || dc.seed_ptr, "layernorm_bwd: dropout needs seed_ptr");
+    int grid = (M + 7) / 8;
+    if (grid > num_sms()) grid = num_sms();
+    const size_t smem = (size_t)8 * H * sizeof(float);
+    if (x_dtype == B200U_BF16)
+        layernorm_bwd_kernel<bf16><<<grid, 256, smem, stream>>>((const bf16*)dy, (const bf16*)x, mean, rstd, gamma, (bf16*)dx, (bf16*)dz, dgamma, dbeta, dbias, M, H, dc);
+    else if (x_dtype == B200U_F32)
+        layernorm_bwd_kernel<float><<<grid, 256, smem, stream>>>((const bf16*)dy, (const float*)x, mean, rstd, gamma, (bf16*)dx, (bf16*)dz, dgamma, dbeta, dbias, M, H, dc);
+    else
+        B200U_CHECK_ARG(false, "layernorm_bwd: unsupported x dtype %d", x_dtype);
+    B200U_CHECK_LAUNCH("layernorm_bwd");
+    return B200U_OK;
+}
+
+extern "C" int b200u_colsum_accum(const void* x, int ldx, float* out, int M, int N,
+                                  b200u_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    B200U_CHECK_ARG(x && out && N % 8 == 0 && ldx % 8 == 0, "colsum_accum: bad arguments");
+    if (M == 0) return B200U_OK;
+    const int gx = (N + 255) / 256;
+    int gy = (2 * num_sms() + gx - 1) / gx;
+    if (gy > (M + 7) / 8) gy = (M + 7) / 8;
+    if (gy < 1) gy = 1;
+    colsum_kernel<<<dim3(gx, gy), 256, 0, stream>>>((const bf16*)x, ldx, out, M, N);
+    B200U_CHECK_LAUNCH("colsum_accum");
+    return B200U_OK;
+}
+
+extern "C" int b200u_cast_f32_to_bf16(const float* x, void* y, size_t n, b200u_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    B200U_CHECK_ARG(x && y && n % 8 == 0, "cast_f32_to_bf16: n must be a multiple of 8");
+    if (n == 0) return B200U_OK;
+    const size_t nvec = n / 8;
+    size_t grid = (nvec + 255) / 256;
+    const size_t cap = (size_t)num_sms() * 16;
+    if (grid > cap) grid = cap;
+    cast_f32_bf16_kernel<<<(int)grid, 256, 0, stream>>>(x, (bf16*)y, nvec);
+    B200U_CHECK_LAUNCH("cast_f32_to_bf16");
+    return B200U_OK;
+}
+
+extern "C" int b200u_gather_rows(const void* txt, const void* img, const long long* gather_index,
+                                 void* out, int B, int T, int R, int L, int H, b200u_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    B200U_CHECK_ARG(txt && img && gather_index && out && H % 8 == 0, "gather_rows: bad arguments");
+    if (B * L == 0) return B200U_OK;
+    gather_rows_kernel<<<(B * L + 7) / 8, 256, 0, stream>>>((const bf16*)txt, (const bf16*)img, gather_index, (bf16*)out, B, T, R, L, H);
+    B200U_CHECK_LAUNCH("gather_rows");
+    return B200U_OK;
+}
+
+extern "C" int b200u_gather_rows_bwd(const void* dout, const long long* gather_index, void* dtxt,
+                                     void* dimg, int B, int T, int R, int L, int H,
+                                     b200u_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    CHECK_H(H);
+    B200U_CHECK_ARG(dout && gather_index && dtxt && dimg, "gather_rows_bwd: null pointer");
+    if (B * (T + R) == 0) return B200U_OK;
+    gather_rows_bwd_kernel<<<(B * (T + R) + 7) / 8, 256, 0, stream>>>((const bf16*)dout, gather_index, (bf16*)dtxt, (bf16*)dimg, B, T, R, L, H);
+    B200U_CHECK_LAUNCH("gather_rows_bwd");
+    return B200U_OK;
+}
