@@ -26,6 +26,8 @@ extern "C" {
 
 typedef void* b200u_stream_t; /* cudaStream_t */
 
+enum { B200U_BF16 = 0, B200U_F32 = 1 };
+
 const char* b200u_last_error_string(void);
 int b200u_version(void);
 /* Compiled SASS arch (100 for sm_100a) and SM count of the current device. */
@@ -77,6 +79,157 @@ typedef struct {
 } b200u_gemm_t;
 
 int b200u_gemm(const b200u_gemm_t* g, b200u_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K5  LayerNorm (Apex FusedLayerNorm(H, eps=1e-12) replacement: model/model.py:229,252,253,258;
+ * model/layer.py:108,149). fwd: y = (x-mean)*rstd*gamma+beta, optional dropout on y, saves
+ * mean/rstd [M] for backward. bwd: dx (bf16), optionally dz = dropout_mask(dx) and
+ * dbias += colsum(dz) for the `LN(dropout(dense(h)) + residual)` pattern
+ * (model/layer.py:111-115,152-156); dgamma/dbeta/dbias are ACCUMULATED (+=) in f32.
+ * drop_on_input != 0: the module is dropout(LN(x)) (embeddings), so dy is masked on load. */
+int b200u_layernorm_fwd(const void* x, int x_dtype, const float* gamma, const float* beta, void* y,
+                        int y_dtype, float* mean, float* rstd, int M, int H, float eps,
+                        const b200u_dropout_t* drop, b200u_stream_t stream);
+int b200u_layernorm_bwd(const void* dy, const void* x, int x_dtype, const float* mean,
+                        const float* rstd, const float* gamma, void* dx, void* dz, float* dgamma,
+                        float* dbeta, float* dbias, int M, int H, const b200u_dropout_t* drop,
+                        int drop_on_input, b200u_stream_t stream);
+
+/* out[n] += sum_m x[m,n] (bf16 in, f32 accumulate): nn.Linear bias gradients. */
+int b200u_colsum_accum(const void* x, int ldx, float* out, int M, int N, b200u_stream_t stream);
+/* y(bf16)[i] = x(f32)[i], n % 8 == 0: img_feat / weight shadow casts. */
+int b200u_cast_f32_to_bf16(const float* x, void* y, size_t n, b200u_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K1  gather_index concat (model/model.py:329-333): out[b,j,:] = cat(txt,img)[b, gather_index[b,j], :]
+ * as 16-byte row copies, bit-exact including padded positions; txt [B,T,H], img [B,R,H],
+ * gather_index int64 [B,L], out [B,L,H], all bf16. bwd = deterministic scatter-add. */
+int b200u_gather_rows(const void* txt, const void* img, const long long* gather_index, void* out,
+                      int B, int T, int R, int L, int H, b200u_stream_t stream);
+int b200u_gather_rows_bwd(const void* dout, const long long* gather_index, void* dtxt, void* dimg,
+                          int B, int T, int R, int L, int H, b200u_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K0  UniterTextEmbeddings.forward (model/model.py:232-245): LN(word[ids]+pos[pos_ids]+type[tids])
+ * then dropout. position_ids may be [B,T] (pos_batch_stride = T) or [1,T] (stride 0);
+ * type_ids NULL -> zeros. sum_out (f32 [B*T,H], pre-LN sum) and mean/rstd feed the backward. */
+int b200u_txt_embed_fwd(const long long* input_ids, const long long* position_ids,
+                        int pos_batch_stride, const long long* type_ids, const float* word,
+                        const float* pos, const float* type, const float* gamma, const float* beta,
+                        void* out, float* sum_out, float* mean, float* rstd, int B, int T, int H,
+                        float eps, const b200u_dropout_t* drop, b200u_stream_t stream);
+/* K2  UniterImageEmbeddings.forward after img_linear (model/model.py:267-271):
+ * LN(LN_img(a) + LN_pos(pos7·Wposᵀ+bpos) + type[type_ids]) then dropout. a = img_linear output
+ * (f32 [n,H], from the GEMM). type_ids NULL -> ones (model/model.py:313-314).
+ * p_out/s_out (f32 [n,H]) and stats_out (f32 [6,n]: mean/rstd of the three LNs) feed the backward. */
+int b200u_img_embed_fwd(const float* a, const float* pos7, const float* Wpos, const float* bpos,
+                        const long long* type_ids, const float* type, const float* g_img,
+                        const float* b_img, const float* g_pos, const float* b_pos, const float* g,
+                        const float* b, void* out, float* p_out, float* s_out, float* stats_out,
+                        int n, int H, float eps, const b200u_dropout_t* drop, b200u_stream_t stream);
+/* nn.Embedding backward: table_grad[id(r), :] += d[r, :] (bf16 rows, f32 atomics). ids NULL ->
+ * every row uses const_id; ids are indexed [b*ids_batch_stride + t] with r = b*T + t. */
+int b200u_embedding_scatter_add(const void* d, const long long* ids, int ids_batch_stride, int T,
+                                long long const_id, float* table_grad, int n, int H,
+                                long long padding_idx, b200u_stream_t stream);
+/* pos_linear weight gradient: dW[h,c] += sum_r dp[r,h] * pos7[r,c]. */
+int b200u_pos_linear_wgrad(const void* dp, const float* pos7, float* dW, int n, int H,
+                           b200u_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K4  BertSelfAttention core (model/layer.py:80-100) on the fused qkv activation [B*L, 3H]:
+ * softmax(Q·Kᵀ/8 + mask) -> dropout -> ·V -> ctx [B*L, H]. mask f32 [B,L] is the ADDITIVE
+ * mask UniterModel.forward builds, (1-attention_mask)*-10000 (model/model.py:342-345), one row
+ * per sample (the [B,1,1,L] broadcast is never materialised). head_dim must be 64, L<=256.
+ * lse f32 [B,heads,L] is saved for the backward, which writes dqkv [B*L, 3H]. */
+int b200u_attention_fwd(const void* qkv, const float* mask, void* ctx, float* lse, int B, int L,
+                        int num_heads, int H, const b200u_dropout_t* drop, b200u_stream_t stream);
+int b200u_attention_bwd(const void* qkv, const float* mask, const void* ctx, const void* dctx,
+                        const float* lse, void* dqkv, int B, int L, int num_heads, int H,
+                        const b200u_dropout_t* drop, b200u_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * BertLayer.forward / its backward as one call each (model/layer.py:159-170). Weight matrices
+ * are the bf16 shadows ([out,in] like nn.Linear.weight; Wqkv = cat(query,key,value).weight),
+ * biases / LayerNorm params f32. `saved` tensors are written by fwd and read by bwd; `grads`
+ * are f32 and ACCUMULATED; `scratch` is reusable across layers. dx0 may alias dx2. */
+typedef struct {
+    int B, L, H, I, heads;
+    float eps;
+    const void* Wqkv; const float* bqkv; /* [3H,H], [3H] */
+    const void* Wo;   const float* bo;   /* [H,H],  [H]  */
+    const float* ln1_g; const float* ln1_b;
+    const void* W1;   const float* b1;   /* [I,H],  [I]  */
+    const void* W2;   const float* b2;   /* [H,I],  [H]  */
+    const float* ln2_g; const float* ln2_b;
+    const float* mask;                   /* f32 [B,L] additive mask (0 / -10000) */
+    float p_attn, p_hidden;              /* dropout probabilities (0 in eval mode) */
+    const unsigned long long* seed;      /* device seed, required when any p > 0 */
+    uint32_t stream_base;                /* RNG stream id of this layer's first dropout site */
+    int gemm_impl;                       /* 0 = tcgen05, 1 = SIMT debug */
+} b200u_layer_params_t;
+typedef struct {
+    void* qkv;  /* bf16 [M,3H] */
+    void* ctx;  /* bf16 [M,H]  */
+    float* lse; /* f32 [B,heads,L] */
+    void* y1;   /* bf16 [M,H] pre-LN1 */
+    float* mean1; float* rstd1;
+    void* x1;   /* bf16 [M,H] LN1 out */
+    void* u;    /* bf16 [M,I] pre-GELU */
+    void* g;    /* bf16 [M,I] post-GELU */
+    void* y2;   /* bf16 [M,H] pre-LN2 */
+    float* mean2; float* rstd2;
+} b200u_layer_saved_t;
+typedef struct {
+    float* dWqkv; float* dbqkv; float* dWo; float* dbo; float* dln1_g; float* dln1_b;
+    float* dW1; float* db1; float* dW2; float* db2; float* dln2_g; float* dln2_b;
+} b200u_layer_grads_t;
+typedef struct {
+    void* dres; /* bf16 [M,H]  */
+    void* dz;   /* bf16 [M,H]  */
+    void* dx1;  /* bf16 [M,H]  */
+    void* dctx; /* bf16 [M,H]  */
+    void* du;   /* bf16 [M,I]  */
+    void* dqkv; /* bf16 [M,3H] */
+} b200u_layer_scratch_t;
+int b200u_bert_layer_fwd(const b200u_layer_params_t* p, const void* x0, const b200u_layer_saved_t* saved,
+                         void* x2, b200u_stream_t stream);
+int b200u_bert_layer_bwd(const b200u_layer_params_t* p, const void* x0, const b200u_layer_saved_t* saved,
+                         const void* dx2, const b200u_layer_grads_t* grads,
+                         const b200u_layer_scratch_t* scratch, void* dx0, b200u_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K7  BertPooler (model/layer.py:179-185), small heads (model/meme_uniter.py:20,
+ * model/pretrain.py:62) and BCEWithLogitsLoss(pos_weight) (train_template.py:64-65,98-99).
+ * h rows are bf16 at h + b*row_stride (first token of sample b); weights f32. Parameter grads
+ * are accumulated (+=). */
+int b200u_pooler_fwd(const void* h, long long row_stride, const float* W, const float* bias,
+                     float* pooled, int B, int H, b200u_stream_t stream);
+int b200u_pooler_bwd(const float* dpooled, const float* pooled, const void* h, long long row_stride,
+                     const float* W, float* dW, float* db, void* dh, long long dh_row_stride, int B,
+                     int H, b200u_stream_t stream);
+int b200u_linear_small_fwd(const float* x, const float* W, const float* bias, float* out, int B,
+                           int C, int K, b200u_stream_t stream);
+int b200u_linear_small_bwd(const float* dout, const float* x, const float* W, float* dx, float* dW,
+                           float* db, int B, int C, int K, b200u_stream_t stream);
+/* loss = mean BCE-with-logits; dlogits = d(loss*grad_scale)/dlogits; probs = sigmoid(logits).
+ * Any of loss/dlogits/probs may be NULL. */
+int b200u_bce_logits(const float* logits, const float* labels, float pos_weight, float grad_scale,
+                     float* loss, float* dlogits, float* probs, int B, b200u_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K10 fused optimizer step over flat f32 buffers (train_template.py:89-107,
+ * utils/optim_utils.py:16-46): grad averaging + clip_grad_norm_ + Adam with L2 weight decay,
+ * refreshing the bf16 weight shadow. lr / step / coef live in device memory (graph replay). */
+int b200u_counter_add(unsigned long long* counter, unsigned long long inc, b200u_stream_t stream);
+int b200u_grad_sumsq(const float* g, size_t n, double* sumsq, b200u_stream_t stream);
+int b200u_clip_coef(const double* sumsq, float pre_scale, float max_norm, float* coef,
+                    float* norm_out, b200u_stream_t stream);
+int b200u_adam_step(float* p, float* g, float* m, float* v, void* shadow_bf16, size_t n,
+                    const long long* run_start, const float* run_wd, const int* chunk_run,
+                    int num_runs, const float* coef, const float* lr,
+                    const unsigned long long* step, float beta1, float beta2, float eps,
+                    int zero_grad, b200u_stream_t stream);
 
 #ifdef __cplusplus
 }

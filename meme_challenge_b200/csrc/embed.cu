@@ -1,0 +1,330 @@
+// K0 / K2 — UNITER text and image embedding kernels (sm_100a).
+//
+//  txt_embed_fwd : LN(word[ids] + pos[position_ids] + type[type_ids]) -> dropout
+//                  (model/model.py:232-245), one warp per token, tables read in fp32.
+//  img_embed_fwd : LN( LN_img(a) + LN_pos(pos7·W_posᵀ + b_pos) + type[type_ids] ) -> dropout
+//                  (model/model.py:261-272; `a` = img_linear output from the tcgen05 GEMM). The
+//                  K=7 pos_linear is 7 FMAs per element on CUDA cores, fused here with the
+//                  three LayerNorms so the 768-wide row is read once and written once.
+//  embedding_scatter_add / pos_linear_wgrad : the parameter-gradient halves of their backward
+//                  (the LayerNorm halves reuse layernorm_bwd from rowops.cu).
+#include "../../include/b200u.h"
+#include "common.cuh"
+
+namespace b200u {
+
+constexpr int EMB_MAXV = 4;  // H <= 1024
+
+__device__ __forceinline__ void ld8f(const float* p, float (&f)[8]) {
+    float4 a = *reinterpret_cast<const float4*>(p);
+    float4 b = *reinterpret_cast<const float4*>(p + 4);
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
+    f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+__device__ __forceinline__ void st8f(float* p, const float (&f)[8]) {
+    *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(f[4], f[5], f[6], f[7]);
+}
+__device__ __forceinline__ void st8b(bf16* p, const float (&f)[8]) {
+    uint4 o;
+    o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]);
+    o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
+    *reinterpret_cast<uint4*>(p) = o;
+}
+
+__device__ __forceinline__ void stats(const float (&x)[EMB_MAXV][8], int nv, int lane, int H,
+                                      float eps, float& mean, float& rstd) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < EMB_MAXV; ++i)
+        if (lane + 32 * i < nv)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s += x[i][j];
+    mean = warp_sum(s) / (float)H;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < EMB_MAXV; ++i)
+        if (lane + 32 * i < nv)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float d = x[i][j] - mean;
+                q += d * d;
+            }
+    rstd = rsqrtf(warp_sum(q) / (float)H + eps);
+}
+
+__device__ __forceinline__ void apply_dropout8(float (&o)[8], uint64_t seed, const DropoutCfg& drop,
+                                               size_t elem0) {
+    if (!drop.thresh16) return;
+    const uint32_t pbase = (uint32_t)(elem0 >> 1);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        uint32_t h = rng_pair(seed, drop.stream, pbase + j);
+        o[2 * j] = ((h & 0xffffu) >= drop.thresh16) ? o[2 * j] * drop.scale : 0.f;
+        o[2 * j + 1] = ((h >> 16) >= drop.thresh16) ? o[2 * j + 1] * drop.scale : 0.f;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+txt_embed_fwd_kernel(const long long* __restrict__ ids, const long long* __restrict__ pos_ids,
+                     int pos_batch_stride, const long long* __restrict__ type_ids,
+                     const float* __restrict__ word, const float* __restrict__ pos,
+                     const float* __restrict__ type, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, bf16* __restrict__ out, float* __restrict__ sum_out,
+                     float* __restrict__ mean_out, float* __restrict__ rstd_out, int n, int T, int H,
+                     float eps, DropoutCfg drop) {
+    const int lane = threadIdx.x & 31;
+    const int tok = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (tok >= n) return;
+    const int b = tok / T, t = tok - b * T;
+    const long long wid = ids[tok];
+    const long long pid = pos_ids[(size_t)b * pos_batch_stride + t];
+    const long long tid = type_ids ? type_ids[tok] : 0;
+    const int nv = H >> 3;
+    float x[EMB_MAXV][8];
+#pragma unroll
+    for (int i = 0; i < EMB_MAXV; ++i) {
+        const int vi = lane + 32 * i;
+        if (vi < nv) {
+            float w[8], p[8], ty[8];
+            ld8f(word + (size_t)wid * H + vi * 8, w);
+            ld8f(pos + (size_t)pid * H + vi * 8, p);
+            ld8f(type + (size_t)tid * H + vi * 8, ty);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) x[i][j] = (w[j] + p[j]) + ty[j];  // model.py:240-242 order
+            if (sum_out) st8f(sum_out + (size_t)tok * H + vi * 8, x[i]);
+        }
+    }
+    float mean, rstd;
+    stats(x, nv, lane, H, eps, mean, rstd);
+    if (lane == 0) {
+        if (mean_out) mean_out[tok] = mean;
+        if (rstd_out) rstd_out[tok] = rstd;
+    }
+    const uint64_t seed = load_seed(drop);
+#pragma unroll
+    for (int i = 0; i < EMB_MAXV; ++i) {
+        const int vi = lane + 32 * i;
+        if (vi < nv) {
+            float g[8], be[8], o[8];
+            ld8f(gamma + vi * 8, g);
+            ld8f(beta + vi * 8, be);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = (x[i][j] - mean) * rstd * g[j] + be[j];
+            apply_dropout8(o, seed, drop, (size_t)tok * H + vi * 8);
+            st8b(out + (size_t)tok * H + vi * 8, o);
+        }
+    }
+}
+
+// stats layout: [6, n] = (mean_img, rstd_img, mean_pos, rstd_pos, mean, rstd) rows
+__global__ void __launch_bounds__(256)
+img_embed_fwd_kernel(const float* __restrict__ a, const float* __restrict__ pos7,
+                     const float* __restrict__ Wpos, const float* __restrict__ bpos,
+                     const long long* __restrict__ type_ids, const float* __restrict__ type,
+                     const float* __restrict__ g_img, const float* __restrict__ b_img,
+                     const float* __restrict__ g_pos, const float* __restrict__ b_pos,
+                     const float* __restrict__ g, const float* __restrict__ be,
+                     bf16* __restrict__ out, float* __restrict__ p_out, float* __restrict__ s_out,
+                     float* __restrict__ stats_out, int n, int H, float eps, DropoutCfg drop) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= n) return;
+    const int nv = H >> 3;
+    float pf[7];
+#pragma unroll
+    for (int c = 0; c < 7; ++c) pf[c] = pos7[(size_t)row * 7 + c];
+    const long long tid = type_ids ? type_ids[row] : 1;  // model.py:313-314 default ones
+
+    float xa[EMB_MAXV][8], xp[EMB_MAXV][8];
+#pragma unroll
+    for (int i = 0; i < EMB_MAXV; ++i) {
+        const int vi = lane + 32 * i;
+        if (vi < nv) {
+            ld8f(a + (size_t)row * H + vi * 8, xa[i]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float* w = Wpos + (size_t)(vi * 8 + j) * 7;
+                float acc = 0.f;
+#pragma unroll
+                for (int c = 0; c < 7; ++c) acc = fmaf(pf[c], w[c], acc);
+                xp[i][j] = acc + bpos[vi * 8 + j];
+            }
+            if (p_out) st8f(p_out + (size_t)row * H + vi * 8, xp[i]);
+        }
+    }
+    float m1, r1, m2, r2, m3, r3;
+    stats(xa, nv, lane, H, eps, m1, r1);
+    stats(xp, nv, lane, H, eps, m2, r2);
+#pragma unroll
+    for (int i = 0; i < EMB_MAXV; ++i) {
+        const int vi = lane + 32 * i;
+        if (vi < nv) {
+            float gi[8], bi[8], gp[8], bp[8], ty[8];
+            ld8f(g_img + vi * 8, gi); ld8f(b_img + vi * 8, bi);
+            ld8f(g_pos + vi * 8, gp); ld8f(b_pos + vi * 8, bp);
+            ld8f(type + (size_t)tid * H + vi * 8, ty);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float t1 = (xa[i][j] - m1) * r1 * gi[j] + bi[j];
+                const float t2 = (xp[i][j] - m2) * r2 * gp[j] + bp[j];
+                xa[i][j] = (t1 + t2) + ty[j];  // model.py:269 order
+            }
+            if (s_out) st8f(s_out + (size_t)row * H + vi * 8, xa[i]);
+        }
+    }
+    stats(xa, nv, lane, H, eps, m3, r3);
+    if (lane == 0 && stats_out) {
+        float* st = stats_out + row;
+        st[0] = m1; st[(size_t)n] = r1; st[(size_t)2 * n] = m2; st[(size_t)3 * n] = r2;
+        st[(size_t)4 * n] = m3; st[(size_t)5 * n] = r3;
+    }
+    const uint64_t seed = load_seed(drop);
+#pragma unroll
+    for (int i = 0; i < EMB_MAXV; ++i) {
+        const int vi = lane + 32 * i;
+        if (vi < nv) {
+            float gg[8], bb[8], o[8];
+            ld8f(g + vi * 8, gg);
+            ld8f(be + vi * 8, bb);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = (xa[i][j] - m3) * r3 * gg[j] + bb[j];
+            apply_dropout8(o, seed, drop, (size_t)row * H + vi * 8);
+            st8b(out + (size_t)row * H + vi * 8, o);
+        }
+    }
+}
+
+// table_grad[ids[r], :] += d[r, :]   (nn.Embedding backward; rows with ids == padding_idx skipped)
+__global__ void __launch_bounds__(256)
+embedding_scatter_add_kernel(const bf16* __restrict__ d, const long long* __restrict__ ids,
+                             int ids_batch_stride, int T, long long const_id, float* __restrict__ table_grad,
+                             int n, int H, long long padding_idx) {
+    const int lane = threadIdx.x & 31;
+    const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= n) return;
+    long long id = const_id;
+    if (ids) {
+        const int b = r / T, t = r - b * T;
+        id = ids[(size_t)b * ids_batch_stride + t];
+    }
+    if (id == padding_idx) return;
+    float* dst = table_grad + (size_t)id * H;
+    for (int v = lane; v < (H >> 3); v += 32) {
+        uint4 u = *reinterpret_cast<const uint4*>(d + (size_t)r * H + v * 8);
+        const uint32_t* up = &u.x;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float2 f = unpack_bf16(up[k]);
+            atomicAdd(dst + v * 8 + 2 * k, f.x);
+            atomicAdd(dst + v * 8 + 2 * k + 1, f.y);
+        }
+    }
+}
+
+// dW[h, c] += sum_r dp[r, h] * pos7[r, c]   (pos_linear weight grad, K = 7). One thread per h.
+__global__ void __launch_bounds__(256)
+pos_linear_wgrad_kernel(const bf16* __restrict__ dp, const float* __restrict__ pos7,
+                        float* __restrict__ dW, int n, int H, int rows_per_block) {
+    const int h = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r0 = blockIdx.y * rows_per_block;
+    const int r1 = min(n, r0 + rows_per_block);
+    __shared__ float sp[64][8];
+    float acc[7];
+#pragma unroll
+    for (int c = 0; c < 7; ++c) acc[c] = 0.f;
+    for (int rb = r0; rb < r1; rb += 64) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < 64 * 7; i += blockDim.x) {
+            const int rr = i / 7, c = i - rr * 7;
+            sp[rr][c] = (rb + rr < r1) ? pos7[(size_t)(rb + rr) * 7 + c] : 0.f;
+        }
+        __syncthreads();
+        if (h < H) {
+            const int cnt = min(64, r1 - rb);
+            for (int rr = 0; rr < cnt; ++rr) {
+                const float v = __bfloat162float(dp[(size_t)(rb + rr) * H + h]);
+#pragma unroll
+                for (int c = 0; c < 7; ++c) acc[c] = fmaf(v, sp[rr][c], acc[c]);
+            }
+        }
+    }
+    if (h < H)
+#pragma unroll
+        for (int c = 0; c < 7; ++c) atomicAdd(dW + (size_t)h * 7 + c, acc[c]);
+}
+
+static DropoutCfg make_drop(const b200u_dropout_t* d) {
+    DropoutCfg c;
+    c.seed_ptr = d ? d->seed_ptr : nullptr;
+    c.stream = d ? d->stream : 0;
+    const float p = d ? d->p : 0.f;
+    c.thresh16 = (uint32_t)(p * 65536.0f + 0.5f);
+    c.scale = 1.0f / (1.0f - p);
+    return c;
+}
+
+}  // namespace b200u
+
+using namespace b200u;
+
+#define CHECK_H(H) \
+    B200U_CHECK_ARG((H) > 0 && (H) % 8 == 0 && (H) <= 8 * 32 * EMB_MAXV, "hidden size %d unsupported (need H%%8==0, H<=1024)", (H))
+
+extern "C" int b200u_txt_embed_fwd(const long long* input_ids, const long long* position_ids,
+                                   int pos_batch_stride, const long long* type_ids, const float* word,
+                                   const float* pos, const float* type, const float* gamma,
+                                   const float* beta, void* out, float* sum_out, float* mean,
+                                   float* rstd, int B, int T, int H, float eps,
+                                   const b200u_dropout_t* drop, b200u_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    CHECK_H(H);
+    B200U_CHECK_ARG(input_ids && position_ids && word && pos && type && gamma && beta && out, "txt_embed_fwd: null pointer");
+    const int n = B * T;
+    if (n == 0) return B200U_OK;
+    DropoutCfg dc = make_drop(drop);
+    B200U_CHECK_ARG(dc.thresh16 == 0 || dc.seed_ptr, "txt_embed_fwd: dropout needs seed_ptr");
+    txt_embed_fwd_kernel<<<(n + 7) / 8, 256, 0, stream>>>(input_ids, position_ids, pos_batch_stride, type_ids, word, pos, type, gamma, beta, (bf16*)out, sum_out, mean, rstd, n, T, H, eps, dc);
+    B200U_CHECK_LAUNCH("txt_embed_fwd");
+    return B200U_OK;
+}
+
+extern "C" int b200u_img_embed_fwd(const float* a, const float* pos7, const float* Wpos,
+                                   const float* bpos, const long long* type_ids, const float* type,
+                                   const float* g_img, const float* b_img, const float* g_pos,
+                                   const float* b_pos, const float* g, const float* b, void* out,
+                                   float* p_out, float* s_out, float* stats_out, int n, int H,
+                                   float eps, const b200u_dropout_t* drop, b200u_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    CHECK_H(H);
+    B200U_CHECK_ARG(a && pos7 && Wpos && bpos && type && g_img && b_img && g_pos && b_pos && g && b && out, "img_embed_fwd: null pointer");
+    if (n == 0) return B200U_OK;
+    DropoutCfg dc = make_drop(drop);
+    B200U_CHECK_ARG(dc.thresh16 == 0 || dc.seed_ptr, "img_embed_fwd: dropout needs seed_ptr");
+    img_embed_fwd_kernel<<<(n + 7) / 8, 256, 0, stream>>>(a, pos7, Wpos, bpos, type_ids, type, g_img, b_img, g_pos, b_pos, g, b, (bf16*)out, p_out, s_out, stats_out, n, H, eps, dc);
+    B200U_CHECK_LAUNCH("img_embed_fwd");
+    return B200U_OK;
+}
+
+extern "C" int b200u_embedding_scatter_add(const void* d, const long long* ids, int ids_batch_stride,
+                                           int T, long long const_id, float* table_grad, int n, int H,
+                                           long long padding_idx, b200u_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    B200U_CHECK_ARG(d && table_grad && H % 8 == 0 && T > 0, "embedding_scatter_add: bad arguments");
+    if (n == 0) return B200U_OK;
+    embedding_scatter_add_kernel<<<(n + 7) / 8, 256, 0, stream>>>((const bf16*)d, ids, ids_batch_stride, T, const_id, table_grad, n, H, padding_idx);
+    B200U_CHECK_LAUNCH("embedding_scatter_add");
+    return B200U_OK;
+}
+
+extern "C" int b200u_pos_linear_wgrad(const void* dp, const float* pos7, float* dW, int n, int H,
+                                      b200u_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    B200U_CHECK_ARG(dp && pos7 && dW, "pos_linear_wgrad: null pointer");
+    if (n == 0) return B200U_OK;
+    const int rows_per_block = 128;
+    dim3 grid((H + 255) / 256, (n + rows_per_block - 1) / rows_per_block);
+    pos_linear_wgrad_kernel<<<grid, 256, 0, stream>>>((const bf16*)dp, pos7, dW, n, H, rows_per_block);
+    B200U_CHECK_LAUNCH("pos_linear_wgrad");
+    return B200U_OK;
+}

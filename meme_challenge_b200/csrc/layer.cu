@@ -1,0 +1,129 @@
+// BertLayer forward / backward as one C call each (model/layer.py:159-170): the launcher strings
+// together the tcgen05 GEMMs, the fused attention and the LayerNorm kernels so the Python side
+// pays one ctypes call per layer and the whole sequence is CUDA-graph capturable.
+//
+// forward (7 launches)                                   reference
+//   qkv = x0·Wqkvᵀ + bqkv                                layer.py:76-78   (one N=3H GEMM)
+//   ctx = attention(qkv, mask)                           layer.py:80-100
+//   y1  = dropout(ctx·Woᵀ + bo) + x0 ; x1 = LN1(y1)      layer.py:111-115
+//   u   = x1·W1ᵀ + b1 ; g = gelu(u)                      layer.py:139-142
+//   y2  = dropout(g·W2ᵀ + b2) + x1 ; x2 = LN2(y2)        layer.py:152-156
+// backward (11 launches): the exact transposes, weight grads accumulated in fp32 (+=).
+#include "../../include/b200u.h"
+#include "common.cuh"
+
+#include <string.h>
+
+using namespace b200u;
+
+namespace {
+
+enum { SITE_ATTN = 0, SITE_HID1 = 1, SITE_HID2 = 2 };
+
+b200u_dropout_t site(const b200u_layer_params_t* p, int which, float prob) {
+    b200u_dropout_t d;
+    d.seed_ptr = p->seed;
+    d.stream = p->stream_base + (uint32_t)which;
+    d.p = prob;
+    return d;
+}
+
+int gemm(int M, int N, int K, const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn,
+         int epi, void* C, int ldc, void* C2, int ldc2, const float* bias, const void* R, int ldr,
+         const b200u_dropout_t* drop, int impl, cudaStream_t stream) {
+    b200u_gemm_t g;
+    memset(&g, 0, sizeof(g));
+    g.M = M; g.N = N; g.K = K;
+    g.A = A; g.lda = lda; g.a_mn_major = a_mn;
+    g.B = B; g.ldb = ldb; g.b_mn_major = b_mn;
+    g.epilogue = epi;
+    g.C = C; g.ldc = ldc; g.C2 = C2; g.ldc2 = ldc2;
+    g.bias = bias; g.R = R; g.ldr = ldr;
+    if (drop) g.drop = *drop;
+    g.impl = impl;
+    return b200u_gemm(&g, stream);
+}
+
+#define TRY(expr)            \
+    do {                     \
+        int _rc = (expr);    \
+        if (_rc) return _rc; \
+    } while (0)
+
+}  // namespace
+
+extern "C" int b200u_bert_layer_fwd(const b200u_layer_params_t* p, const void* x0,
+                                    const b200u_layer_saved_t* s, void* x2, b200u_stream_t stream_) {
+    cudaStream_t st = (cudaStream_t)stream_;
+    B200U_CHECK_ARG(p && x0 && s && x2, "bert_layer_fwd: null pointer");
+    const int M = p->B * p->L, H = p->H, I = p->I;
+    if (M == 0) return B200U_OK;
+    const b200u_dropout_t d_attn = site(p, SITE_ATTN, p->p_attn);
+    const b200u_dropout_t d_h1 = site(p, SITE_HID1, p->p_hidden);
+    const b200u_dropout_t d_h2 = site(p, SITE_HID2, p->p_hidden);
+
+    TRY(gemm(M, 3 * H, H, x0, H, 0, p->Wqkv, H, 0, B200U_EPI_STORE, s->qkv, 3 * H, nullptr, 0, p->bqkv,
+             nullptr, 0, nullptr, p->gemm_impl, st));
+    TRY(b200u_attention_fwd(s->qkv, p->mask, s->ctx, s->lse, p->B, p->L, p->heads, H, &d_attn, st));
+    TRY(gemm(M, H, H, s->ctx, H, 0, p->Wo, H, 0, B200U_EPI_BIAS_DROP_RES, s->y1, H, nullptr, 0, p->bo, x0,
+             H, &d_h1, p->gemm_impl, st));
+    TRY(b200u_layernorm_fwd(s->y1, B200U_BF16, p->ln1_g, p->ln1_b, s->x1, B200U_BF16, s->mean1, s->rstd1,
+                            M, H, p->eps, nullptr, st));
+    TRY(gemm(M, I, H, s->x1, H, 0, p->W1, H, 0, B200U_EPI_BIAS_GELU, s->u, I, s->g, I, p->b1, nullptr, 0,
+             nullptr, p->gemm_impl, st));
+    TRY(gemm(M, H, I, s->g, I, 0, p->W2, I, 0, B200U_EPI_BIAS_DROP_RES, s->y2, H, nullptr, 0, p->b2, s->x1,
+             H, &d_h2, p->gemm_impl, st));
+    TRY(b200u_layernorm_fwd(s->y2, B200U_BF16, p->ln2_g, p->ln2_b, x2, B200U_BF16, s->mean2, s->rstd2, M,
+                            H, p->eps, nullptr, st));
+    return B200U_OK;
+}
+
+extern "C" int b200u_bert_layer_bwd(const b200u_layer_params_t* p, const void* x0,
+                                    const b200u_layer_saved_t* s, const void* dx2,
+                                    const b200u_layer_grads_t* g, const b200u_layer_scratch_t* w,
+                                    void* dx0, b200u_stream_t stream_) {
+    cudaStream_t st = (cudaStream_t)stream_;
+    B200U_CHECK_ARG(p && x0 && s && dx2 && g && w && dx0, "bert_layer_bwd: null pointer");
+    const int M = p->B * p->L, H = p->H, I = p->I;
+    if (M == 0) return B200U_OK;
+    const b200u_dropout_t d_attn = site(p, SITE_ATTN, p->p_attn);
+    const b200u_dropout_t d_h1 = site(p, SITE_HID1, p->p_hidden);
+    const b200u_dropout_t d_h2 = site(p, SITE_HID2, p->p_hidden);
+    const int impl = p->gemm_impl;
+
+    // LN2 backward: dres (= grad of x1 through the residual) and dz2 (= grad of the FFN2 output)
+    void* dz2 = p->p_hidden > 0.f ? w->dz : w->dres;
+    TRY(b200u_layernorm_bwd(dx2, s->y2, B200U_BF16, s->mean2, s->rstd2, p->ln2_g, w->dres,
+                            p->p_hidden > 0.f ? w->dz : nullptr, g->dln2_g, g->dln2_b, g->db2, M, H, &d_h2,
+                            0, st));
+    // FFN2: dW2[H,I] += dz2ᵀ·g ; du = (dz2·W2) * gelu'(u)
+    TRY(gemm(H, I, M, dz2, H, 1, s->g, I, 1, B200U_EPI_ATOMIC_F32, g->dW2, I, nullptr, 0, nullptr, nullptr,
+             0, nullptr, impl, st));
+    TRY(gemm(M, I, H, dz2, H, 0, p->W2, I, 1, B200U_EPI_DGELU, w->du, I, nullptr, 0, nullptr, s->u, I,
+             nullptr, impl, st));
+    TRY(b200u_colsum_accum(w->du, I, g->db1, M, I, st));
+    // FFN1: dW1[I,H] += duᵀ·x1 ; dx1 = du·W1 + dres
+    TRY(gemm(I, H, M, w->du, I, 1, s->x1, H, 1, B200U_EPI_ATOMIC_F32, g->dW1, H, nullptr, 0, nullptr,
+             nullptr, 0, nullptr, impl, st));
+    TRY(gemm(M, H, I, w->du, I, 0, p->W1, H, 1, B200U_EPI_ADD, w->dx1, H, nullptr, 0, nullptr, w->dres, H,
+             nullptr, impl, st));
+    // LN1 backward
+    void* dz1 = p->p_hidden > 0.f ? w->dz : w->dres;
+    TRY(b200u_layernorm_bwd(w->dx1, s->y1, B200U_BF16, s->mean1, s->rstd1, p->ln1_g, w->dres,
+                            p->p_hidden > 0.f ? w->dz : nullptr, g->dln1_g, g->dln1_b, g->dbo, M, H, &d_h1,
+                            0, st));
+    // attention output projection: dWo[H,H] += dz1ᵀ·ctx ; dctx = dz1·Wo
+    TRY(gemm(H, H, M, dz1, H, 1, s->ctx, H, 1, B200U_EPI_ATOMIC_F32, g->dWo, H, nullptr, 0, nullptr,
+             nullptr, 0, nullptr, impl, st));
+    TRY(gemm(M, H, H, dz1, H, 0, p->Wo, H, 1, B200U_EPI_STORE, w->dctx, H, nullptr, 0, nullptr, nullptr, 0,
+             nullptr, impl, st));
+    TRY(b200u_attention_bwd(s->qkv, p->mask, s->ctx, w->dctx, s->lse, w->dqkv, p->B, p->L, p->heads, H,
+                            &d_attn, st));
+    TRY(b200u_colsum_accum(w->dqkv, 3 * H, g->dbqkv, M, 3 * H, st));
+    // QKV projection: dWqkv[3H,H] += dqkvᵀ·x0 ; dx0 = dqkv·Wqkv + dres
+    TRY(gemm(3 * H, H, M, w->dqkv, 3 * H, 1, x0, H, 1, B200U_EPI_ATOMIC_F32, g->dWqkv, H, nullptr, 0,
+             nullptr, nullptr, 0, nullptr, impl, st));
+    TRY(gemm(M, H, 3 * H, w->dqkv, 3 * H, 0, p->Wqkv, H, 1, B200U_EPI_ADD, dx0, H, nullptr, 0, nullptr,
+             w->dres, H, nullptr, impl, st));
+    return B200U_OK;
+}

@@ -128,7 +128,7 @@ layernorm_bwd_kernel(const bf16* __restrict__ dy, const TX* __restrict__ x,
                      const float* __restrict__ mean, const float* __restrict__ rstd,
                      const float* __restrict__ gamma, bf16* __restrict__ dx, bf16* __restrict__ dz,
                      float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias,
-                     int M, int H, DropoutCfg drop) {
+                     int M, int H, DropoutCfg drop, int drop_on_input) {
     extern __shared__ float red[];  // [warps][H]
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -154,6 +154,16 @@ layernorm_bwd_kernel(const bf16* __restrict__ dy, const TX* __restrict__ x,
                 load8(x + (size_t)row * H + vi * 8, xh[i]);
                 load8(dy + (size_t)row * H + vi * 8, d);
                 load8(gamma + vi * 8, g);
+                if (drop_on_input && drop.thresh16) {
+                    // y = dropout(LN(x)) (embedding modules): the incoming grad is masked first
+                    const uint32_t pbase = (uint32_t)(((size_t)row * H + vi * 8) >> 1);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        uint32_t h = rng_pair(seed, drop.stream, pbase + j);
+                        d[2 * j] = ((h & 0xffffu) >= drop.thresh16) ? d[2 * j] * drop.scale : 0.f;
+                        d[2 * j + 1] = ((h >> 16) >= drop.thresh16) ? d[2 * j + 1] * drop.scale : 0.f;
+                    }
+                }
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     xh[i][j] = (xh[i][j] - mu) * rs;
@@ -176,7 +186,7 @@ layernorm_bwd_kernel(const bf16* __restrict__ dy, const TX* __restrict__ x,
                 for (int j = 0; j < 8; ++j) o[j] = rs * (gd[i][j] - s1 - xh[i][j] * s2);
                 if (dx) store8(dx + (size_t)row * H + vi * 8, o);
                 if (dz) {
-                    if (drop.thresh16) {
+                    if (drop.thresh16 && !drop_on_input) {
                         const uint32_t pbase = (uint32_t)(((size_t)row * H + vi * 8) >> 1);
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
@@ -367,7 +377,8 @@ extern "C" int b200u_layernorm_fwd(const void* x, int x_dtype, const float* gamm
 extern "C" int b200u_layernorm_bwd(const void* dy, const void* x, int x_dtype, const float* mean,
                                    const float* rstd, const float* gamma, void* dx, void* dz,
                                    float* dgamma, float* dbeta, float* dbias, int M, int H,
-                                   const b200u_dropout_t* drop, b200u_stream_t stream_) {
+                                   const b200u_dropout_t* drop, int drop_on_input,
+                                   b200u_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     CHECK_H(H);
     B200U_CHECK_ARG(dy && x && mean && rstd && gamma, "layernorm_bwd: null pointer");
@@ -379,9 +390,9 @@ extern "C" int b200u_layernorm_bwd(const void* dy, const void* x, int x_dtype, c
     if (grid > num_sms()) grid = num_sms();
     const size_t smem = (size_t)8 * H * sizeof(float);
     if (x_dtype == B200U_BF16)
-        layernorm_bwd_kernel<bf16><<<grid, 256, smem, stream>>>((const bf16*)dy, (const bf16*)x, mean, rstd, gamma, (bf16*)dx, (bf16*)dz, dgamma, dbeta, dbias, M, H, dc);
+        layernorm_bwd_kernel<bf16><<<grid, 256, smem, stream>>>((const bf16*)dy, (const bf16*)x, mean, rstd, gamma, (bf16*)dx, (bf16*)dz, dgamma, dbeta, dbias, M, H, dc, drop_on_input);
     else if (x_dtype == B200U_F32)
-        layernorm_bwd_kernel<float><<<grid, 256, smem, stream>>>((const bf16*)dy, (const float*)x, mean, rstd, gamma, (bf16*)dx, (bf16*)dz, dgamma, dbeta, dbias, M, H, dc);
+        layernorm_bwd_kernel<float><<<grid, 256, smem, stream>>>((const bf16*)dy, (const float*)x, mean, rstd, gamma, (bf16*)dx, (bf16*)dz, dgamma, dbeta, dbias, M, H, dc, drop_on_input);
     else
         B200U_CHECK_ARG(false, "layernorm_bwd: unsupported x dtype %d", x_dtype);
     B200U_CHECK_LAUNCH("layernorm_bwd");

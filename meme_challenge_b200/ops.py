@@ -53,3 +53,96 @@ def gemm(a, b, *, a_mn=False, b_mn=False, epilogue=EPI_STORE, out=None, out2=Non
     g.splits, g.block_n, g.impl = splits, block_n, impl
     _lib.check(_lib.lib().b200u_gemm(C.byref(g), _lib.stream_ptr()), "b200u_gemm")
     return (out, out2) if epilogue == EPI_BIAS_GELU else out
+
+
+# --------------------------------------------------------------------------------------------
+def _dt(t):
+    if t.dtype == torch.bfloat16:
+        return 0
+    if t.dtype == torch.float32:
+        return 1
+    raise _lib.B200UError("unsupported dtype %s" % t.dtype)
+
+
+def _drop_ref(drop):
+    return C.byref(drop) if drop is not None else None
+
+
+def _call(name, *args):
+    _lib.check(getattr(_lib.lib(), name)(*args, _lib.stream_ptr()), name)
+
+
+P = _lib.ptr
+
+
+def layernorm_fwd(x, gamma, beta, eps, out_dtype=None, drop=None, want_stats=True):
+    H = x.shape[-1]
+    M = x.numel() // H
+    assert x.is_contiguous()
+    y = torch.empty(x.shape, device=x.device, dtype=out_dtype or x.dtype)
+    mean = torch.empty(M, device=x.device, dtype=torch.float32) if want_stats else None
+    rstd = torch.empty(M, device=x.device, dtype=torch.float32) if want_stats else None
+    _call("b200u_layernorm_fwd", P(x), _dt(x), P(gamma), P(beta), P(y), _dt(y), P(mean), P(rstd), M, H,
+          float(eps), _drop_ref(drop))
+    return y, mean, rstd
+
+
+def layernorm_bwd(dy, x, mean, rstd, gamma, dgamma, dbeta, *, want_dx=True, dz=False, dbias=None,
+                  drop=None, drop_on_input=False):
+    H = x.shape[-1]
+    M = x.numel() // H
+    assert dy.dtype == torch.bfloat16 and dy.is_contiguous() and x.is_contiguous()
+    dx = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16) if want_dx else None
+    dzt = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16) if dz else None
+    _call("b200u_layernorm_bwd", P(dy), P(x), _dt(x), P(mean), P(rstd), P(gamma), P(dx), P(dzt),
+          P(dgamma), P(dbeta), P(dbias), M, H, _drop_ref(drop), int(drop_on_input))
+    return dx, dzt
+
+
+def colsum_accum(x, out):
+    assert x.dtype == torch.bfloat16 and x.dim() == 2 and out.dtype == torch.float32
+    _call("b200u_colsum_accum", P(x), x.stride(0), P(out), x.shape[0], x.shape[1])
+
+
+def cast_f32_to_bf16(x, y):
+    assert x.dtype == torch.float32 and y.dtype == torch.bfloat16 and x.numel() == y.numel()
+    assert x.is_contiguous() and y.is_contiguous()
+    _call("b200u_cast_f32_to_bf16", P(x), P(y), C.c_size_t(x.numel()))
+    return y
+
+
+def gather_rows(txt, img, gather_index):
+    B, T, H = txt.shape
+    R = img.shape[1]
+    L = gather_index.shape[1]
+    assert gather_index.dtype == torch.int64 and gather_index.is_contiguous()
+    out = torch.empty(B, L, H, device=txt.device, dtype=torch.bfloat16)
+    _call("b200u_gather_rows", P(txt), P(img), P(gather_index), P(out), B, T, R, L, H)
+    return out
+
+
+def gather_rows_bwd(dout, gather_index, T, R):
+    B, L, H = dout.shape
+    dtxt = torch.empty(B, T, H, device=dout.device, dtype=torch.bfloat16)
+    dimg = torch.empty(B, R, H, device=dout.device, dtype=torch.bfloat16)
+    _call("b200u_gather_rows_bwd", P(dout), P(gather_index), P(dtxt), P(dimg), B, T, R, L, H)
+    return dtxt, dimg
+
+
+def attention_fwd(qkv, mask, B, L, heads, H, drop=None, want_lse=True):
+    ctx = torch.empty(B * L, H, device=qkv.device, dtype=torch.bfloat16)
+    lse = torch.empty(B, heads, L, device=qkv.device, dtype=torch.float32) if want_lse else None
+    _call("b200u_attention_fwd", P(qkv), P(mask), P(ctx), P(lse), B, L, heads, H, _drop_ref(drop))
+    return ctx, lse
+
+
+def attention_bwd(qkv, mask, ctx, dctx, lse, B, L, heads, H, drop=None):
+    dqkv = torch.empty_like(qkv)
+    _call("b200u_attention_bwd", P(qkv), P(mask), P(ctx), P(dctx), P(lse), P(dqkv), B, L, heads, H,
+          _drop_ref(drop))
+    return dqkv
+
+
+def counter_add(counter, inc):
+    assert counter.dtype == torch.int64
+    _call("b200u_counter_add", P(counter), C.c_ulonglong(inc))
