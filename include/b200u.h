@@ -32,6 +32,13 @@ const char* b200u_last_error_string(void);
 int b200u_version(void);
 /* Compiled SASS arch (100 for sm_100a) and SM count of the current device. */
 int b200u_device_info(int* sm_count, int* cc_major, int* cc_minor);
+/* Number of kernels this library has launched in the process so far (bench.py gpu_launches). */
+long long b200u_launch_count(void);
+/* Event-time every tcgen05 GEMM launch (bench.py roofline leg). enable(n) arms up to n records,
+ * collect() synchronises and returns summed duration / algorithmic FLOPs (2MNK) / record count.
+ * Must not be armed during CUDA-graph capture. */
+int b200u_prof_enable(int max_records);
+int b200u_prof_collect(double* total_ms, double* total_flops, int* count);
 
 /* ------------------------------------------------------------------------------------------
  * Dropout configuration shared by all fused-dropout kernels (torch nn.Dropout sites:

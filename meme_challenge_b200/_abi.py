@@ -17,6 +17,9 @@ SIGNATURES = {
     "b200u_last_error_string": (C.c_char_p, []),
     "b200u_version": (_i, []),
     "b200u_device_info": (_i, [C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
+    "b200u_launch_count": (_ll, []),
+    "b200u_prof_enable": (_i, [_i]),
+    "b200u_prof_collect": (_i, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_i)]),
     "b200u_gemm": (_i, [_p, _p]),
     "b200u_layernorm_fwd": (_i, [_p, _i, _p, _p, _p, _i, _p, _p, _i, _i, _f, _p, _p]),
     "b200u_layernorm_bwd": (_i, [_p, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p, _i, _p]),

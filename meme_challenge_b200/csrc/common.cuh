@@ -31,8 +31,11 @@ void set_error(const char* fmt, ...);
         }                                                              \
     } while (0)
 
+void count_launch();  // bumps the kernel-launch counter read by b200u_launch_count()
+
 #define B200U_CHECK_LAUNCH(name)                                                        \
     do {                                                                                \
+        ::b200u::count_launch();                                                        \
         cudaError_t _e = cudaGetLastError();                                            \
         if (_e != cudaSuccess) {                                                        \
             ::b200u::set_error("%s: launch failed: %s", name, cudaGetErrorString(_e));  \
@@ -49,6 +52,8 @@ void set_error(const char* fmt, ...);
         }                                                                                    \
     } while (0)
 
+bool prof_begin(cudaStream_t st, double flops, int* slot);
+void prof_end(cudaStream_t st, int slot);
 int num_sms();  // cached cudaDevAttrMultiProcessorCount of the current device
 
 typedef __nv_bfloat16 bf16;

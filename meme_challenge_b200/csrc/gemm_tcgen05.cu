@@ -437,7 +437,10 @@ static int launch_tc(const b200u_gemm_t* d, GemmArgs& g, cudaStream_t stream) {
                                               Cfg::SMEM_BYTES));
         attr_set = true;
     }
+    int slot = 0;
+    const bool prof = prof_begin(stream, 2.0 * d->M * d->N * d->K, &slot);
     kern<<<grid, 256, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, g);
+    if (prof) prof_end(stream, slot);
     B200U_CHECK_LAUNCH("gemm_tc_kernel");
     return B200U_OK;
 }

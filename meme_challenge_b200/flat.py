@@ -128,14 +128,18 @@ class FlatStore(object):
         return buf[off:off + rows * per_row].view((rows,) + tuple(first.shape[1:]))
 
     # ------------------------------------------------------------------ shadow / grads
+    def version_sig(self):
+        # in-place updates through optimizers / load_state_dict / copy_ bump each param's version
+        return sum(e[1]._version for e in self.entries)
+
     def refresh_shadow(self, force=False):
-        v = self.flat._version
+        v = self.version_sig()
         if force or self._shadow_version != v:
             ops.cast_f32_to_bf16(self.flat, self.shadow)
             self._shadow_version = v
 
     def mark_shadow_current(self):
-        self._shadow_version = self.flat._version
+        self._shadow_version = self.version_sig()
 
     def attach_grads(self):
         """Make every param.grad the flat-buffer view again (after zero_grad(set_to_none=True))."""

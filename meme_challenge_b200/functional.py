@@ -34,6 +34,7 @@ class Runtime(object):
         self.p_attn = p_attn if training else 0.0
         self.gemm_impl = gemm_impl
         self.eps = eps
+        self.layer_cb = None
 
     def drop(self, stream_id, p):
         return _lib.dropout_t(self.seed, stream_id, p)
@@ -235,7 +236,7 @@ class TxtEmbedFn(torch.autograd.Function):
         if token_type_ids is not None:
             token_type_ids = token_type_ids.contiguous()
         out = torch.empty(B, T, H, device=dev, dtype=torch.bfloat16)
-        need = torch.is_grad_enabled()
+        need = any(ctx.needs_input_grad)  # grad mode is off inside Function.forward
         sum_out = torch.empty(B * T, H, device=dev, dtype=torch.float32) if need else None
         mean = torch.empty(B * T, device=dev, dtype=torch.float32) if need else None
         rstd = torch.empty(B * T, device=dev, dtype=torch.float32) if need else None
@@ -300,7 +301,7 @@ class ImgEmbedFn(torch.autograd.Function):
         if img_type_ids is not None:
             img_type_ids = img_type_ids.contiguous()
         out = torch.empty(B, R, H, device=dev, dtype=torch.bfloat16)
-        need = torch.is_grad_enabled()
+        need = any(ctx.needs_input_grad)  # grad mode is off inside Function.forward
         p_out = torch.empty(n, H, device=dev, dtype=torch.float32) if need else None
         s_out = torch.empty(n, H, device=dev, dtype=torch.float32) if need else None
         stats = torch.empty(6, n, device=dev, dtype=torch.float32) if need else None
@@ -389,7 +390,8 @@ class PoolerFn(torch.autograd.Function):
         weight, bias = ctx.params
         B, L, H = hidden.shape
         dh = torch.zeros_like(hidden)
-        ops._call("b200u_pooler_bwd", P(dpooled.contiguous().float()), P(pooled), P(hidden),
+        dpooled = dpooled.contiguous().float()  # keep a reference until after the launch
+        ops._call("b200u_pooler_bwd", P(dpooled), P(pooled), P(hidden),
                   C.c_longlong(L * H), P(weight), P(grad_buf(weight)), P(grad_buf(bias)), P(dh),
                   C.c_longlong(L * H), B, H)
         return dh, None, None
@@ -416,8 +418,10 @@ class SmallLinearFn(torch.autograd.Function):
         B, K = x.shape
         Cn = weight.shape[0]
         dx = torch.empty_like(x)
-        ops._call("b200u_linear_small_bwd", P(dout.contiguous().float()), P(x), P(weight), P(dx),
-                  P(grad_buf(weight)), P(grad_buf(bias) if bias is not None else None), B, Cn, K)
+        dout = dout.contiguous().float()  # keep a reference until after the launch
+        gw = grad_buf(weight)
+        gb = grad_buf(bias) if bias is not None else None
+        ops._call("b200u_linear_small_bwd", P(dout), P(x), P(weight), P(dx), P(gw), P(gb), B, Cn, K)
         return dx, None, None
 
 

@@ -203,7 +203,11 @@ class UniterEncoder(nn.Module):
     def forward(self, input_, attention_mask, output_all_encoded_layers=True, _rt=None):
         all_encoder_layers = []
         hidden_states = input_
+        cb = getattr(_rt, "layer_cb", None)
         for i, layer_module in enumerate(self.layer):
+            if cb is not None and hidden_states.requires_grad:
+                # fires once the backward of layer i is enqueued (train.py gradient buckets)
+                hidden_states.register_hook(lambda g, i=i, cb=cb: cb(i))
             hidden_states = layer_module(hidden_states, attention_mask, _rt=_rt, _layer_idx=i,
                                          _infer_cache=self._infer_cache)
             if output_all_encoded_layers:
@@ -238,13 +242,10 @@ class UniterModel(UniterPreTrainedModel):
 
     def _runtime(self):
         st = self._store.ensure()
-        sig = sum(e[1]._version for e in st.entries)
-        if st._shadow_version != sig:
-            ops.cast_f32_to_bf16(st.flat, st.shadow)
-            st._shadow_version = sig
+        st.refresh_shadow()
         training = self.training
         seed = None
-        if training and torch.is_grad_enabled():
+        if torch.is_grad_enabled():
             st.attach_grads()
         if training and (self.config.hidden_dropout_prob > 0 or self.config.attention_probs_dropout_prob > 0):
             if self._seed_state is None or self._seed_state.device != st.flat.device:
@@ -252,8 +253,10 @@ class UniterModel(UniterPreTrainedModel):
                 self._seed_state = torch.tensor([s0], device=st.flat.device, dtype=torch.int64)
             seed = self._seed_state.clone()
             ops.counter_add(self._seed_state, 0x9E3779B97F4A7C15)
-        return F_.Runtime(st, training, seed, self.config.hidden_dropout_prob,
-                          self.config.attention_probs_dropout_prob, self.gemm_impl)
+        rt = F_.Runtime(st, training, seed, self.config.hidden_dropout_prob,
+                        self.config.attention_probs_dropout_prob, self.gemm_impl)
+        rt.layer_cb = getattr(self, "_layer_grad_ready_cb", None)
+        return rt
 
     # ---------------------------------------------------------------- reference API
     def _compute_txt_embeddings(self, input_ids, position_ids, txt_type_ids=None, _rt=None):

@@ -1,0 +1,198 @@
+"""Fused fine-tuning step for MemeUniter on b200u kernels, single GPU or data parallel.
+
+Semantics are the reference trainer's (train_template.py:89-109, utils/optim_utils.py:16-46):
+every micro-batch runs forward + `loss.backward()`; once `gradient_accumulation` micro-batches
+are in, gradients are divided by the accumulation count, clipped to `max_grad_norm` (global L2),
+Adam with L2 weight decay (no decay for names containing 'bias' / 'LayerNorm.bias' /
+'LayerNorm.weight') updates the fp32 master weights, and the gradients are zeroed. What changes is
+the mechanics: one flat gradient buffer, a three-launch optimizer (sum of squares, clip
+coefficient, fused Adam that also refreshes the bf16 weight shadow), the whole step captured in
+one CUDA graph, and — with world_size > 1 — one process per GPU with per-layer gradient buckets
+all-reduced by NCCL over NVLink while the backward of earlier layers is still running (instead
+of nn.DataParallel's per-step parameter broadcast + gradient reduce, train_template.py:58-59).
+"""
+import ctypes as C
+import math
+
+import torch
+
+from . import _lib, ops
+from . import functional as F_
+from .flat import FlatStore
+
+P = _lib.ptr
+
+NO_DECAY = ['bias', 'LayerNorm.bias', 'LayerNorm.weight']  # utils/optim_utils.py:16
+
+
+def cosine_with_warmup(step, warmup_steps, total_steps):
+    """transformers.get_cosine_schedule_with_warmup multiplier (train_template.py:80-82)."""
+    if step < warmup_steps:
+        return float(step) / float(max(1, warmup_steps))
+    progress = float(step - warmup_steps) / float(max(1, total_steps - warmup_steps))
+    return max(0.0, 0.5 * (1.0 + math.cos(math.pi * progress)))
+
+
+class TrainStep(object):
+    def __init__(self, model, lr=3e-5, weight_decay=1e-3, betas=(0.9, 0.999), eps=1e-8,
+                 gradient_accumulation=2, max_grad_norm=5.0, pos_wt=1.8, process_group=None,
+                 overlap_comm=True):
+        self.model = model
+        self.um = model.uniter_model
+        self.accum = int(gradient_accumulation)
+        self.max_grad_norm = float(max_grad_norm)
+        self.pos_wt = float(pos_wt)
+        self.betas, self.eps = betas, eps
+        self.pg = process_group
+        self.world = 1
+        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            self.world = torch.distributed.get_world_size(process_group)
+        self.overlap_comm = overlap_comm
+
+        # one flat store for the whole MemeUniter (UNITER + classification head)
+        store = FlatStore(model)
+        self.um._store = store
+        store.ensure()
+        self.store = store
+        dev = store.flat.device
+        self.dev = dev
+        n = store.flat.numel()
+        self.m = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.v = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.lr_t = torch.tensor([lr], device=dev, dtype=torch.float32)
+        self.step_t = torch.zeros(1, device=dev, dtype=torch.int64)
+        self.sumsq = torch.zeros(1, device=dev, dtype=torch.float64)
+        self.coef = torch.ones(1, device=dev, dtype=torch.float32)
+        self.gnorm = torch.zeros(1, device=dev, dtype=torch.float32)
+        self.base_lr = lr
+        self.host_step = 0
+
+        # weight-decay runs over the flat layout
+        starts, wds = [], []
+        for name, p, off, cnt in store.entries:
+            wd = 0.0 if any(nd in name for nd in NO_DECAY) else float(weight_decay)
+            if not wds or wds[-1] != wd:
+                starts.append(off)
+                wds.append(wd)
+        starts[0] = 0
+        self.run_start = torch.tensor(starts + [n], device=dev, dtype=torch.int64)
+        self.run_wd = torch.tensor(wds, device=dev, dtype=torch.float32)
+        nchunks = (n + 1023) // 1024
+        chunk_first = torch.arange(nchunks, dtype=torch.int64) * 1024
+        cr = torch.searchsorted(torch.tensor(starts, dtype=torch.int64), chunk_first, right=True) - 1
+        self.chunk_run = cr.to(torch.int32).to(dev)
+        self.num_runs = len(wds)
+
+        # gradient buckets in backward order: [head + pooler + last layer], ..., layer 0, embeddings
+        self.buckets = self._make_buckets()
+        self._pending = []
+        self._graph = None
+        self._static = None
+        self.um._layer_grad_ready_cb = None
+        store.refresh_shadow(force=True)
+
+    # ------------------------------------------------------------------ buckets / comm
+    def _make_buckets(self):
+        ent = self.store.entries
+        first_layer = {}
+        for i, (name, p, off, cnt) in enumerate(ent):
+            if ".encoder.layer." in name or name.startswith("encoder.layer."):
+                l = int(name.split("encoder.layer.")[1].split(".")[0])
+                first_layer.setdefault(l, off)
+        n = self.store.flat.numel()
+        layers = sorted(first_layer)
+        cuts = [first_layer[l] for l in layers]          # start offset of each layer
+        bounds = [0] + cuts + [n]
+        # segments: [0, layer0) = embeddings ; [layer_i, layer_{i+1}) ; [last layer, n) incl. pooler/head
+        segs = [(bounds[i], bounds[i + 1]) for i in range(len(bounds) - 1)]
+        return segs  # index 0 = embeddings, 1.. = layers (last one also holds pooler + head)
+
+    def _allreduce_bucket(self, seg):
+        lo, hi = seg
+        if hi <= lo:
+            return
+        w = torch.distributed.all_reduce(self.store.grad[lo:hi], group=self.pg, async_op=True)
+        self._pending.append(w)
+
+    def _on_layer_done(self, layer_idx):
+        # called (from the autograd thread) once the backward of encoder layer `layer_idx` has been
+        # enqueued: its bucket is final for this optimizer step, start the all-reduce now
+        self._allreduce_bucket(self.buckets[layer_idx + 1])
+
+    # ------------------------------------------------------------------ one micro-batch
+    def micro_step(self, batch, last):
+        kw = dict(input_ids=batch["input_ids"], position_ids=batch["position_ids"],
+                  img_feat=batch["img_feat"], img_pos_feat=batch["img_pos_feat"],
+                  attention_mask=batch["attn_mask"], gather_index=batch["gather_index"],
+                  output_all_encoded_layers=False)
+        comm = self.world > 1 and last
+        self.um._layer_grad_ready_cb = self._on_layer_done if (comm and self.overlap_comm) else None
+        logits = self.model(**kw)
+        loss, dlogits, probs = F_.bce_with_logits(logits, batch["labels"], self.pos_wt)
+        torch.autograd.backward(logits, dlogits.view_as(logits))
+        self.um._layer_grad_ready_cb = None
+        if comm:
+            if not self.overlap_comm:
+                for seg in reversed(self.buckets[1:]):
+                    self._allreduce_bucket(seg)
+            self._allreduce_bucket(self.buckets[0])
+        return loss, probs
+
+    # ------------------------------------------------------------------ optimizer
+    def optimizer_step(self):
+        for w in self._pending:
+            w.wait()
+        self._pending = []
+        g = self.store.grad
+        n = g.numel()
+        self.sumsq.zero_()
+        ops._call("b200u_grad_sumsq", P(g), C.c_size_t(n), P(self.sumsq))
+        pre = 1.0 / (self.accum * self.world)  # average_gradients + mean over ranks
+        ops._call("b200u_clip_coef", P(self.sumsq), pre, self.max_grad_norm, P(self.coef), P(self.gnorm))
+        ops.counter_add(self.step_t, 1)
+        ops._call("b200u_adam_step", P(self.store.flat), P(g), P(self.m), P(self.v), P(self.store.shadow),
+                  C.c_size_t(n), P(self.run_start), P(self.run_wd), P(self.chunk_run), self.num_runs,
+                  P(self.coef), P(self.lr_t), P(self.step_t), self.betas[0], self.betas[1], self.eps, 1)
+
+    def set_lr(self, lr):
+        self.lr_t.fill_(lr)
+
+    # ------------------------------------------------------------------ public: one optimizer step
+    def step(self, batches):
+        """batches: list of `gradient_accumulation` device batch dicts. Returns the list of
+        (loss[1], probs[B]) device tensors of the micro-batches."""
+        assert len(batches) == self.accum
+        outs = []
+        for i, b in enumerate(batches):
+            outs.append(self.micro_step(b, last=(i == len(batches) - 1)))
+        self.optimizer_step()
+        self.host_step += 1
+        return outs
+
+    # ------------------------------------------------------------------ CUDA-graph replay
+    def capture(self, example_batches, warmup=3):
+        """Capture one full optimizer step (all micro-batches + optimizer) in a CUDA graph over
+        static input buffers. Returns the static buffers; fill them and call replay()."""
+        static = [{k: v.clone() for k, v in b.items() if torch.is_tensor(v)} for b in example_batches]
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(warmup):
+                self.step(static)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            outs = self.step(static)
+        self._graph, self._static, self._static_out = graph, static, outs
+        return static
+
+    def load_static(self, batches):
+        for dst, src in zip(self._static, batches):
+            for k, v in dst.items():
+                v.copy_(src[k], non_blocking=True)
+
+    def replay(self):
+        self._graph.replay()
+        self.host_step += 1
+        return self._static_out

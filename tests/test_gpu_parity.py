@@ -1,0 +1,388 @@
+"""GPU (-m gpu): the CUDA path, called through the C-ABI, against the CPU oracle on the same seeded
+inputs. Tolerances are BASELINE.json's: gather/mask bit-exact; logits max-abs <= 1e-2; loss rel
+<= 1e-3 (bf16 compute / fp32 accumulate)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import uniter_oracle as O
+from oracle.make_golden import IMG_DIM, TINY
+
+DEV = "cuda"
+LOGIT_TOL = 1e-2     # BASELINE.json north_star
+LOSS_RTOL = 1e-3     # BASELINE.json north_star
+
+
+def _require_gpu():
+    assert torch.cuda.is_available(), "gpu tests need a CUDA device"
+    from meme_challenge_b200 import _lib
+    import ctypes
+    sm, ma, mi = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    _lib.check(_lib.lib().b200u_device_info(ctypes.byref(sm), ctypes.byref(ma), ctypes.byref(mi)))
+    assert ma.value == 10, "built for sm_100a, found cc %d.%d" % (ma.value, mi.value)
+
+
+def _cos(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return float((a @ b) / (a.norm() * b.norm() + 1e-30))
+
+
+# ----------------------------------------------------------------------------------------------
+# kernels
+# ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True), (True, False)])
+@pytest.mark.parametrize("shape", [(128, 128, 64), (2624, 768, 768), (200, 136, 72), (768, 3072, 2624)])
+def test_gemm_layouts(shape, a_mn, b_mn):
+    _require_gpu()
+    from meme_challenge_b200 import ops
+    M, N, K = shape
+    torch.manual_seed(1)
+    a = torch.randn((K, M) if a_mn else (M, K), device=DEV).bfloat16()
+    b = torch.randn((K, N) if b_mn else (N, K), device=DEV).bfloat16()
+    ref = (a.float().t() if a_mn else a.float()).cpu() @ (b.float() if b_mn else b.float().t()).cpu()
+    for bn in (128, 256):
+        out = ops.gemm(a, b, a_mn=a_mn, b_mn=b_mn, block_n=bn).float().cpu()
+        assert (out - ref).abs().max() <= 1e-2 * ref.abs().max()
+
+
+def test_gemm_epilogues_and_splitk():
+    _require_gpu()
+    from meme_challenge_b200 import _lib, ops
+    M, N, K = 520, 384, 320
+    torch.manual_seed(2)
+    a = torch.randn(M, K, device=DEV).bfloat16()
+    b = torch.randn(N, K, device=DEV).bfloat16()
+    bias = torch.randn(N, device=DEV)
+    res = torch.randn(M, N, device=DEV).bfloat16()
+    ref = a.float().cpu() @ b.float().cpu().t()
+    tol = 1e-2 * ref.abs().max()
+    u, g = ops.gemm(a, b, bias=bias, epilogue=_lib.EPI_BIAS_GELU)
+    assert (u.float().cpu() - (ref + bias.cpu())).abs().max() <= tol
+    assert (g.float().cpu() - O.gelu(u.float().cpu())).abs().max() <= 1e-2 * O.gelu(ref).abs().max()
+    out = ops.gemm(a, b, bias=bias, res=res, epilogue=_lib.EPI_BIAS_DROP_RES)
+    assert (out.float().cpu() - (ref + bias.cpu() + res.float().cpu())).abs().max() <= tol
+    x = res.float().cpu().requires_grad_(True)
+    O.gelu(x).sum().backward()
+    out = ops.gemm(a, b, res=res, epilogue=_lib.EPI_DGELU)
+    assert (out.float().cpu() - ref * x.grad).abs().max() <= tol
+    acc = torch.full((M, N), 2.0, device=DEV)
+    ops.gemm(a, b, epilogue=_lib.EPI_ATOMIC_F32, out=acc, splits=3)
+    assert (acc.cpu() - (ref + 2.0)).abs().max() <= 2e-3 * ref.abs().max()
+    # tcgen05 path and the SIMT debug path share the epilogue: results agree to fp32 rounding
+    o0 = ops.gemm(a, b, bias=bias, epilogue=_lib.EPI_STORE_F32, impl=0)
+    o1 = ops.gemm(a, b, bias=bias, epilogue=_lib.EPI_STORE_F32, impl=1)
+    assert (o0 - o1).abs().max() <= 1e-3 * ref.abs().max()
+
+
+def test_gemm_dropout_statistics():
+    _require_gpu()
+    from meme_challenge_b200 import _lib, ops
+    M, N, K = 1024, 768, 64
+    a = torch.ones(M, K, device=DEV).bfloat16()
+    b = torch.ones(N, K, device=DEV).bfloat16()
+    zero = torch.zeros(M, N, device=DEV).bfloat16()
+    seed = torch.tensor([42], device=DEV, dtype=torch.int64)
+    d = _lib.dropout_t(seed, 5, 0.1)
+    o = ops.gemm(a, b, bias=torch.zeros(N, device=DEV), res=zero, epilogue=_lib.EPI_BIAS_DROP_RES, drop=d).float()
+    keep = (o != 0).float().mean().item()
+    assert abs(keep - 0.9) < 3e-3
+    assert torch.allclose(o[o != 0], torch.tensor(64.0 / 0.9, device=DEV), rtol=1e-2)
+    seed2 = torch.tensor([43], device=DEV, dtype=torch.int64)
+    o2 = ops.gemm(a, b, bias=torch.zeros(N, device=DEV), res=zero, epilogue=_lib.EPI_BIAS_DROP_RES,
+                  drop=_lib.dropout_t(seed2, 5, 0.1)).float()
+    agree = ((o != 0) == (o2 != 0)).float().mean().item()
+    assert abs(agree - 0.82) < 0.01  # independent masks: 0.9^2 + 0.1^2
+
+
+@pytest.mark.parametrize("H", [128, 768, 1024])
+def test_layernorm_fwd_bwd(H):
+    _require_gpu()
+    from meme_challenge_b200 import ops
+    torch.manual_seed(3)
+    M = 777
+    x = (torch.randn(M, H) * 2 + 0.5)
+    w, b = torch.randn(H) * 0.3 + 1, torch.randn(H) * 0.1
+    dy = torch.randn(M, H)
+    xb, dyb = x.bfloat16(), dy.bfloat16()
+    xr = xb.float().requires_grad_(True)
+    wr, br = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    yr = O.layer_norm(xr, wr, br)
+    yr.backward(dyb.float())
+    y, mean, rstd = ops.layernorm_fwd(xb.to(DEV), w.to(DEV), b.to(DEV), 1e-12)
+    assert (y.float().cpu() - yr.detach()).abs().max() < 3e-2
+    dg, db_, dbias = (torch.zeros(H, device=DEV) for _ in range(3))
+    dx, _ = ops.layernorm_bwd(dyb.to(DEV), xb.to(DEV), mean, rstd, w.to(DEV), dg, db_, dbias=dbias)
+    assert _cos(dx.float().cpu(), xr.grad) > 0.9999
+    assert (dx.float().cpu() - xr.grad).abs().max() < 2e-2 * xr.grad.abs().max()
+    assert torch.allclose(dg.cpu(), wr.grad, rtol=1e-3, atol=1e-2)
+    assert torch.allclose(db_.cpu(), br.grad, rtol=1e-3, atol=1e-2)
+    assert torch.allclose(dbias.cpu(), dx.float().sum(0).cpu(), rtol=1e-3, atol=1e-2)
+
+
+def test_gather_bit_exact_with_padded_positions():
+    """K1: torch.equal with model/model.py:330-333 on identical inputs, identity tail included."""
+    _require_gpu()
+    from meme_challenge_b200 import ops
+    torch.manual_seed(4)
+    B, T, R, H = 5, 16, 20, 128
+    tl = [16, 3, 9, 1, 12]
+    nb = [20, 20, 4, 7, 13]
+    am = O.get_attention_mask(tl, nb)
+    L = am.shape[1]
+    gi = O.get_gather_index(tl, nb, B, T, L)
+    txt = torch.randn(B, T, H).bfloat16()
+    img = torch.randn(B, R, H).bfloat16()
+    want = torch.gather(torch.cat([txt, img], 1), 1, gi.unsqueeze(-1).expand(-1, -1, H))
+    got = ops.gather_rows(txt.to(DEV), img.to(DEV), gi.to(DEV)).cpu()
+    assert torch.equal(got.view(torch.int16), want.view(torch.int16))
+    # backward == scatter-add (duplicates in the identity tail add up)
+    dout = torch.randn(B, L, H).bfloat16()
+    cat = torch.cat([txt, img], 1).float().requires_grad_(True)
+    torch.gather(cat, 1, gi.unsqueeze(-1).expand(-1, -1, H)).backward(dout.float())
+    dtxt, dimg = ops.gather_rows_bwd(dout.to(DEV), gi.to(DEV), T, R)
+    got_g = torch.cat([dtxt, dimg], 1).float().cpu()
+    assert (got_g - cat.grad).abs().max() <= 2e-2 * cat.grad.abs().max()
+
+
+def test_index_mask_on_device_bit_exact():
+    _require_gpu()
+    from meme_challenge_b200.utils.utils import get_attention_mask, get_gather_index
+    tl, nb, T = [8, 64, 33, 1], [100, 36, 77, 50], 64
+    am = get_attention_mask(tl, nb, device=DEV)
+    gi = get_gather_index(tl, nb, 4, T, am.shape[1], device=DEV)
+    assert torch.equal(am.cpu(), O.get_attention_mask(tl, nb))
+    assert torch.equal(gi.cpu(), O.get_gather_index(tl, nb, 4, T, am.shape[1]))
+
+
+@pytest.mark.parametrize("L,heads", [(164, 12), (76, 2), (40, 3), (200, 2)])
+def test_attention_fwd_bwd(L, heads):
+    _require_gpu()
+    from meme_challenge_b200 import ops
+    torch.manual_seed(5)
+    B, H = 3, heads * 64
+    qkv = (torch.randn(B * L, 3 * H) * 0.8).bfloat16()
+    valid = torch.tensor([L, max(1, L // 2), max(1, L - 7)])
+    mask01 = (torch.arange(L).unsqueeze(0) < valid.unsqueeze(1)).float()
+    mask_add = (1.0 - mask01) * -10000.0
+    dctx = torch.randn(B * L, H).bfloat16()
+
+    x = qkv.float().requires_grad_(True)
+    q, k, v = x.view(B, L, 3, heads, 64).permute(2, 0, 3, 1, 4)
+    s = q @ k.transpose(-1, -2) / 8.0 + mask_add[:, None, None, :]
+    ctx_ref = (torch.softmax(s, -1) @ v).permute(0, 2, 1, 3).reshape(B * L, H)
+    ctx_ref.backward(dctx.float())
+
+    ctx, lse = ops.attention_fwd(qkv.to(DEV), mask_add.to(DEV), B, L, heads, H)
+    assert (ctx.float().cpu() - ctx_ref.detach()).abs().max() < 2e-2
+    dqkv = ops.attention_bwd(qkv.to(DEV), mask_add.to(DEV), ctx, dctx.to(DEV), lse, B, L, heads, H)
+    g = dqkv.float().cpu()
+    assert _cos(g, x.grad) > 0.999
+    assert (g - x.grad).abs().max() < 3e-2 * x.grad.abs().max()
+    # masked keys receive exactly zero dK / dV, like the reference (exp underflow)
+    gk = g.view(B, L, 3, H)[1, int(valid[1]):, 1:]
+    assert gk.abs().max() == 0
+
+
+def test_attention_dropout_is_consistent_between_fwd_and_bwd():
+    """With dropout on, d(ctx)/d(V) must use the same mask the forward drew: check the linearity
+    ctx(V1 + V2) == ctx(V1) + ctx(V2) for a fixed seed, and the backward against a finite
+    difference through V."""
+    _require_gpu()
+    from meme_challenge_b200 import _lib, ops
+    torch.manual_seed(6)
+    B, L, heads = 2, 100, 2
+    H = heads * 64
+    qkv = (torch.randn(B * L, 3 * H) * 0.5).bfloat16().to(DEV)
+    mask_add = torch.zeros(B, L, device=DEV)
+    seed = torch.tensor([99], device=DEV, dtype=torch.int64)
+    d = _lib.dropout_t(seed, 3, 0.1)
+    ctx1, lse = ops.attention_fwd(qkv, mask_add, B, L, heads, H, drop=d)
+    ctx2, _ = ops.attention_fwd(qkv, mask_add, B, L, heads, H, drop=d)
+    assert torch.equal(ctx1, ctx2)  # same seed -> same mask
+    ctx0, _ = ops.attention_fwd(qkv, mask_add, B, L, heads, H)
+    assert not torch.equal(ctx0, ctx1)
+    # E[dropout(P)] = P: averaged over rows the dropped context stays close to the clean one
+    assert (ctx1.float().mean(0) - ctx0.float().mean(0)).abs().max() < 0.05
+    # backward: dV = Pdᵀ·dO. With dO = one-hot rows, compare against forward differences in V.
+    dctx = torch.zeros(B * L, H, device=DEV).bfloat16()
+    dctx[5, 7] = 1.0
+    dqkv = ops.attention_bwd(qkv, mask_add, ctx1, dctx, lse, B, L, heads, H, drop=d).float()
+    dv = dqkv[:L, 2 * H + 7]          # d ctx[5, 7] / d V[j, 7] for sample 0, head 0  == Pd[5, j]
+    q2 = qkv.clone().float()
+    q2[:L, 2 * H:2 * H + 64] = 0
+    q2[:L, 2 * H + 7] = torch.arange(L, device=DEV).float() % 2  # V[:, 7] = parity pattern
+    c, _ = ops.attention_fwd(q2.bfloat16(), mask_add, B, L, heads, H, drop=d)
+    want = (dv * (torch.arange(L, device=DEV).float() % 2)).sum()
+    assert abs(c[5, 7].float().item() - want.item()) < 2e-2
+
+
+# ----------------------------------------------------------------------------------------------
+# whole model against the reference golden vectors and the oracle
+# ----------------------------------------------------------------------------------------------
+def _build(cfg_dict, img_dim, sd=None, seed=0):
+    from meme_challenge_b200.model.meme_uniter import MemeUniter
+    from meme_challenge_b200.model.model import UniterConfig, UniterModel
+    torch.manual_seed(seed)
+    cfg = UniterConfig.from_dict(cfg_dict)
+    m = MemeUniter(UniterModel(cfg, img_dim), cfg.hidden_size, 1)
+    if sd is not None:
+        m.load_state_dict(sd, strict=True)
+    return m.to(DEV)
+
+
+def _kw(b, dev=DEV):
+    return dict(input_ids=b["input_ids"].to(dev), position_ids=b["position_ids"].to(dev),
+                img_feat=b["img_feat"].to(dev), img_pos_feat=b["img_pos_feat"].to(dev),
+                attention_mask=b["attn_mask"].to(dev), gather_index=b["gather_index"].to(dev),
+                output_all_encoded_layers=False)
+
+
+def test_tiny_model_against_reference_golden(golden_dir):
+    """Committed fixtures from the unmodified reference: logits, loss and every parameter grad."""
+    _require_gpu()
+    g = np.load(os.path.join(golden_dir, "tiny_meme_uniter.npz"))
+    sd = {k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd.")}
+    b = {k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("in.")}
+    m = _build(TINY, IMG_DIM, sd).eval()
+    logits = m(**_kw(b))
+    assert logits.dtype == torch.float32 and tuple(logits.shape) == (4, 1)
+    assert (logits.detach().cpu().numpy() - g["logits"]).__abs__().max() <= LOGIT_TOL
+    loss = torch.nn.BCEWithLogitsLoss(pos_weight=torch.tensor([1.8], device=DEV))(
+        logits.squeeze(1), b["labels"].float().to(DEV))
+    assert abs(loss.item() - float(g["loss"])) <= LOSS_RTOL * abs(float(g["loss"]))
+    loss.backward()
+    worst = 1.0
+    for n, p in m.named_parameters():
+        key = "grad." + n
+        if key not in g.files:
+            assert p.grad is None or p.grad.abs().max() == 0, n
+            continue
+        want = torch.from_numpy(g[key])
+        got = p.grad.detach().cpu()
+        if want.abs().max() < 1e-7:
+            continue
+        c = _cos(got, want)
+        worst = min(worst, c)
+        assert c > 0.99, (n, c)
+    assert worst > 0.99
+    # intermediate tensors: embedding output and per-layer outputs on valid rows
+    layers = m.uniter_model(**{**_kw(b), "output_all_encoded_layers": True})
+    assert len(layers) == 2
+    valid = b["attn_mask"].bool()
+    for got, key in ((layers[0], "layer0_out"), (layers[1], "layer1_out")):
+        d = (got.float().cpu() - torch.from_numpy(g[key])).abs()
+        assert d[valid].max() < 5e-2
+
+
+def _oracle_run(m, cfg_dict, b, pos_wt=1.8, want_grads=True):
+    sd = {k: v.detach().float().cpu().clone().requires_grad_(want_grads) for k, v in m.state_dict().items()}
+    kw = dict(input_ids=b["input_ids"], position_ids=b["position_ids"], img_feat=b["img_feat"],
+              img_pos_feat=b["img_pos_feat"], attention_mask=b["attn_mask"], gather_index=b["gather_index"])
+    with torch.set_grad_enabled(want_grads):
+        logits = O.meme_uniter_forward(sd, cfg_dict, **kw)
+        loss = O.bce_loss(logits, b["labels"], pos_wt)
+    if want_grads:
+        loss.backward()
+    return logits.detach(), loss.detach(), sd
+
+
+BASE = dict(vocab_size=28996, hidden_size=768, num_hidden_layers=12, num_attention_heads=12,
+            intermediate_size=3072, hidden_act="gelu", hidden_dropout_prob=0.1,
+            attention_probs_dropout_prob=0.1, max_position_embeddings=512, type_vocab_size=2,
+            initializer_range=0.02)
+
+
+def test_base_c1_inference_logits():
+    """BASELINE config 1: UNITER-base inference, B=16, 36 regions, 40 tokens (L=76)."""
+    _require_gpu()
+    b = O.synth_batch(16, 40, 36, seed=1234)
+    m = _build(BASE, 2048).eval()
+    with torch.no_grad():
+        logits = m(**_kw(b)).cpu()
+    ref, _, _ = _oracle_run(m, BASE, b, want_grads=False)
+    assert (logits - ref).abs().max() <= LOGIT_TOL
+
+
+@pytest.mark.parametrize("variable", [False, True])
+def test_base_c2_fwd_bwd_against_oracle(variable):
+    """BASELINE config 2 shape: B=16, 100 regions, 64 tokens (L=164), fwd+bwd, pos_wt 1.8 BCE
+    (dropout off for parity). Fixed and ragged (36-100 regions) batches."""
+    _require_gpu()
+    b = O.synth_batch(16, 64, 100, seed=1234 + int(variable), variable=variable)
+    m = _build(BASE, 2048).eval()
+    logits = m(**_kw(b))
+    loss = torch.nn.BCEWithLogitsLoss(pos_weight=torch.tensor([1.8], device=DEV))(
+        logits.squeeze(1), b["labels"].float().to(DEV))
+    loss.backward()
+    ref_logits, ref_loss, sd = _oracle_run(m, BASE, b)
+    assert (logits.detach().cpu() - ref_logits).abs().max() <= LOGIT_TOL
+    assert abs(loss.item() - ref_loss.item()) <= LOSS_RTOL * abs(ref_loss.item())
+    bad = []
+    for n, p in m.named_parameters():
+        want = sd[n].grad
+        if want is None or want.abs().max() < 1e-8:
+            continue
+        c = _cos(p.grad.detach().cpu(), want)
+        if c < 0.98:
+            bad.append((n, c))
+    assert not bad, bad[:8]
+    # whole-gradient agreement
+    names = [n for n, p in m.named_parameters() if sd[n].grad is not None]
+    got = torch.cat([dict(m.named_parameters())[n].grad.detach().cpu().flatten() for n in names])
+    want = torch.cat([sd[n].grad.flatten() for n in names])
+    assert _cos(got, want) > 0.995
+    assert abs(got.norm().item() / want.norm().item() - 1) < 2e-2
+
+
+def test_state_dict_roundtrip_with_oracle():
+    """save -> oracle load -> same logits; and fused buffers still export separate q/k/v."""
+    _require_gpu()
+    m = _build(TINY, IMG_DIM).eval()
+    b = O.synth_batch(3, 10, 6, seed=5, variable=True, img_dim=IMG_DIM, vocab=TINY["vocab_size"], min_txt=2, min_bb=2)
+    with torch.no_grad():
+        l0 = m(**_kw(b)).cpu()
+    sd = {k: v.cpu().clone() for k, v in m.state_dict().items()}
+    assert "uniter_model.encoder.layer.0.attention.self.key.weight" in sd
+    ref, _, _ = _oracle_run(m, TINY, b, want_grads=False)
+    assert (l0 - ref).abs().max() <= LOGIT_TOL
+    m2 = _build(TINY, IMG_DIM, sd, seed=123).eval()
+    with torch.no_grad():
+        l1 = m2(**_kw(b)).cpu()
+    assert torch.equal(l0, l1)
+
+
+def test_training_mode_dropout_runs_and_differs():
+    _require_gpu()
+    m = _build(TINY, IMG_DIM).train()
+    b = O.synth_batch(4, 12, 10, seed=2, img_dim=IMG_DIM, vocab=TINY["vocab_size"], min_txt=2, min_bb=2)
+    l1 = m(**_kw(b))
+    l2 = m(**_kw(b))
+    assert not torch.equal(l1, l2)  # fresh masks per forward
+    l2.sum().backward()
+    g = m.uniter_model.encoder.layer[0].attention.self.query.weight.grad
+    assert g is not None and torch.isfinite(g).all() and g.abs().max() > 0
+
+
+def test_grad_accumulation_and_zero_grad_set_to_none():
+    """Two backward passes accumulate like the reference's `elif grad_step: loss.backward()`
+    (train_template.py:108-109); zero_grad(set_to_none=True) is survived."""
+    _require_gpu()
+    m = _build(TINY, IMG_DIM).eval()
+    b = O.synth_batch(4, 12, 10, seed=3, img_dim=IMG_DIM, vocab=TINY["vocab_size"], min_txt=2, min_bb=2)
+    m(**_kw(b)).sum().backward()
+    w = m.uniter_model.encoder.layer[1].output.dense.weight
+    g1 = w.grad.clone()
+    m(**_kw(b)).sum().backward()
+    assert torch.allclose(w.grad, 2 * g1, rtol=1e-3, atol=1e-6)
+    opt = torch.optim.Adam(m.parameters(), lr=1e-3)
+    opt.zero_grad(set_to_none=True)
+    m(**_kw(b)).sum().backward()
+    assert torch.allclose(w.grad, g1, rtol=1e-3, atol=1e-6)
+    opt.step()
+    with torch.no_grad():
+        l_after = m(**_kw(b))
+    assert torch.isfinite(l_after).all()
