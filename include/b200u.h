@@ -83,9 +83,14 @@ typedef struct {
     int splits;             /* split-K factor, >1 only with EPI_ATOMIC_F32; 0 = auto */
     int block_n;            /* 0 = auto, else 128 or 256 */
     int impl;               /* 0 = tcgen05 (product path), 1 = SIMT debug kernel */
+    int cluster;            /* 0 = auto, 1 = no cluster, 2 = CTA pairs with TMA-multicast B tiles */
 } b200u_gemm_t;
 
 int b200u_gemm(const b200u_gemm_t* g, b200u_stream_t stream);
+/* Bring-up aid: non-NULL -> every tcgen05 GEMM CTA writes 8 clock64() phase stamps (int64) to
+ * device_ptr[cta*8 ..] (entry, setup done, TMA issued, first operands landed, MMAs issued,
+ * accumulator ready, epilogue done, exit). NULL disables. */
+int b200u_gemm_debug_stamps(long long* device_ptr);
 
 /* ------------------------------------------------------------------------------------------
  * K5  LayerNorm (Apex FusedLayerNorm(H, eps=1e-12) replacement: model/model.py:229,252,253,258;

@@ -21,6 +21,7 @@ SIGNATURES = {
     "b200u_prof_enable": (_i, [_i]),
     "b200u_prof_collect": (_i, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_i)]),
     "b200u_gemm": (_i, [_p, _p]),
+    "b200u_gemm_debug_stamps": (_i, [_p]),
     "b200u_layernorm_fwd": (_i, [_p, _i, _p, _p, _p, _i, _p, _p, _i, _i, _f, _p, _p]),
     "b200u_layernorm_bwd": (_i, [_p, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p, _i, _p]),
     "b200u_colsum_accum": (_i, [_p, _i, _p, _i, _i, _p]),

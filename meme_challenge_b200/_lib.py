@@ -34,7 +34,7 @@ class GemmT(C.Structure):
         ("bias", C.c_void_p),
         ("R", C.c_void_p), ("ldr", C.c_int),
         ("drop", DropoutT),
-        ("splits", C.c_int), ("block_n", C.c_int), ("impl", C.c_int),
+        ("splits", C.c_int), ("block_n", C.c_int), ("impl", C.c_int), ("cluster", C.c_int),
     ]
 
 

@@ -92,12 +92,26 @@ __device__ __forceinline__ uint64_t load_seed(const DropoutCfg& d) {
 // ---------------------------------------------------------------------------------------
 // Small math helpers (reference: model/layer.py:31-37 exact erf GELU).
 // ---------------------------------------------------------------------------------------
+// erf via Abramowitz-Stegun 7.1.26 (|abs error| <= 1.5e-7, i.e. fp32-level for GELU): one
+// reciprocal, one exp2 and five FMAs instead of erff()'s ~40-instruction polynomial, so the fused
+// GEMM epilogues stay cheaper than the main loop they overlap with.
+__device__ __forceinline__ float erf_fast(float x) {
+    const float ax = fabsf(x);
+    const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+    float p = fmaf(1.061405429f, t, -1.453152027f);
+    p = fmaf(p, t, 1.421413741f);
+    p = fmaf(p, t, -0.284496736f);
+    p = fmaf(p, t, 0.254829592f);
+    const float e = exp2f(-1.4426950408889634f * ax * ax);
+    const float r = fmaf(-p * t, e, 1.0f);
+    return copysignf(r, x);
+}
 __device__ __forceinline__ float gelu_erf(float x) {
-    return x * 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+    return x * 0.5f * (1.0f + erf_fast(x * 0.70710678118654752440f));
 }
 __device__ __forceinline__ float gelu_erf_grad(float x) {
-    float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
-    float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
+    float cdf = 0.5f * (1.0f + erf_fast(x * 0.70710678118654752440f));
+    float pdf = 0.39894228040143267794f * exp2f(-0.72134752044448170368f * x * x);
     return cdf + x * pdf;
 }
 
@@ -172,6 +186,63 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tmap, 
         ::"r"(smem_u32(dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
+// smem (swizzled box) -> global, bulk-group completion; OOB parts of the box are clipped.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tmap, const void* src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tmap),
+                 "r"(smem_u32(src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+// global += smem box (element-wise add in the tensor map's data type, performed at L2).
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* tmap, const void* src, int c0, int c1) {
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tmap),
+                 "r"(smem_u32(src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_all() {
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// Multicast variant: the box lands at the same smem offset in every CTA of `cta_mask` and
+// completes transaction bytes on the mbarrier at the same offset in each of them.
+__device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* tmap, uint64_t* bar,
+                                               int c0, int c1, uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+        "[%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(cta_mask)
+        : "memory");
+}
+// tcgen05.commit that arrives on the barrier at this offset in every CTA of `cta_mask`.
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t cta_mask) {
+    asm volatile(
+        "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+        ::"r"(smem_u32(bar)), "h"(cta_mask)
+        : "memory");
+}
+// true in exactly one (converged) lane of the warp
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tmap) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
 }

@@ -28,7 +28,14 @@ struct GemmArgs {
     const float* bias;
     const bf16* R; int ldr;
     DropoutCfg drop;
+    long long* dbg;  // optional per-CTA phase timestamps (8 x int64 per CTA), bring-up only
+    int dbg_mode;    // bring-up: 1 = skip the MMAs (TMA-only), 2 = skip the TMA loads (MMA-only)
 };
+
+#define DBG_STAMP(slot)                                                     \
+    do {                                                                    \
+        if (g.dbg) g.dbg[(size_t)blockIdx.x * 8 + (slot)] = clock64();      \
+    } while (0)
 
 // ---------------------------------------------------------------------------------------
 // Fused epilogue for one output row, 32 consecutive columns starting at col0.
@@ -164,6 +171,11 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
     d |= (uint64_t)2 << 61;  // SWIZZLE_128B
     return d;
 }
+// descriptor without the start address (constant per operand layout)
+__host__ __device__ constexpr uint64_t desc_template(uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) |
+           ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
 // instruction descriptor for kind::f16, bf16 x bf16 -> f32.
 __host__ __device__ constexpr uint32_t make_idesc(int m, int n, bool a_mn, bool b_mn) {
     return (1u << 4)                      // D format f32
@@ -175,77 +187,160 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n, bool a_mn, bool 
            | ((uint32_t)(m >> 4) << 24);  // M
 }
 
-template <int BLOCK_N>
+constexpr int EPI_WARPS = 8;                      // warps 4..11
+constexpr int GEMM_THREADS = (4 + EPI_WARPS) * 32;  // 384
+
+template <int BLOCK_N, int EPI>
 struct GemmCfg {
+    static constexpr bool HAS_R = EPI == B200U_EPI_BIAS_DROP_RES || EPI == B200U_EPI_ADD || EPI == B200U_EPI_DGELU;
+    static constexpr bool DUAL = EPI == B200U_EPI_BIAS_GELU;
+    static constexpr bool F32_OUT = EPI == B200U_EPI_ATOMIC_F32 || EPI == B200U_EPI_STORE_F32;
+    static constexpr bool HAS_BIAS = EPI == B200U_EPI_STORE || EPI == B200U_EPI_BIAS_GELU ||
+                                     EPI == B200U_EPI_BIAS_DROP_RES || EPI == B200U_EPI_STORE_F32;
+    static constexpr int GROUP_COLS = F32_OUT ? 32 : 64;  // one 128-byte swizzled row per output group
+    static constexpr int NUM_GROUPS = BLOCK_N / GROUP_COLS;
     static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
     static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
-    static constexpr int STAGES = (BLOCK_N >= 256) ? 4 : 6;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STG_PER_WARP = 4096 * (DUAL ? 2 : 1);
+    static constexpr int STG_BYTES = EPI_WARPS * STG_PER_WARP;
+    static constexpr int R_BYTES = HAS_R ? BLOCK_M * BLOCK_N * 2 : 0;
+    static constexpr int BIAS_BYTES = EPI_WARPS * BLOCK_N * 4;
+    static constexpr int FIXED = 1024 /*align*/ + STG_BYTES + R_BYTES + BIAS_BYTES + 256 /*barriers*/;
+    static constexpr int STAGES_RAW = (232448 - FIXED) / STAGE_BYTES;
+    static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
+    static_assert(STAGES >= 2, "not enough shared memory for a pipelined main loop");
+    static constexpr int SMEM_BYTES = FIXED + STAGES * STAGE_BYTES;
     static constexpr int TMEM_COLS = 2 * BLOCK_N;  // two accumulator stages
-    static constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + 1024 /*align*/ + 256 /*bars*/;
 };
 
-template <int BLOCK_N, bool A_MN, bool B_MN, int EPI>
-__global__ void __launch_bounds__(256, 1)
+// Epilogue math for 8 consecutive columns of one row (bf16 outputs).
+template <int EPI>
+__device__ __forceinline__ void epi_math8(float (&v)[8], float (&w)[8], const float* bias8, uint4 rraw,
+                                          const GemmArgs& g, uint64_t seed, int row, int col) {
+    if (EPI == B200U_EPI_STORE || EPI == B200U_EPI_BIAS_GELU || EPI == B200U_EPI_BIAS_DROP_RES) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] += bias8[i];
+    }
+    float r[8];
+    if (EPI == B200U_EPI_BIAS_DROP_RES || EPI == B200U_EPI_ADD || EPI == B200U_EPI_DGELU) {
+        float2 f;
+        f = unpack_bf16(rraw.x); r[0] = f.x; r[1] = f.y;
+        f = unpack_bf16(rraw.y); r[2] = f.x; r[3] = f.y;
+        f = unpack_bf16(rraw.z); r[4] = f.x; r[5] = f.y;
+        f = unpack_bf16(rraw.w); r[6] = f.x; r[7] = f.y;
+    }
+    if (EPI == B200U_EPI_BIAS_DROP_RES) {
+        if (g.drop.thresh16) {
+            const uint32_t pbase = (uint32_t)(((size_t)row * g.N + col) >> 1);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                uint32_t h = rng_pair(seed, g.drop.stream, pbase + i);
+                v[2 * i] = ((h & 0xffffu) >= g.drop.thresh16) ? v[2 * i] * g.drop.scale : 0.f;
+                v[2 * i + 1] = ((h >> 16) >= g.drop.thresh16) ? v[2 * i + 1] * g.drop.scale : 0.f;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] += r[i];
+    } else if (EPI == B200U_EPI_ADD) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] += r[i];
+    } else if (EPI == B200U_EPI_DGELU) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] *= gelu_erf_grad(r[i]);
+    } else if (EPI == B200U_EPI_BIAS_GELU) {
+        // GELU of the bf16-rounded pre-activation: backward sees exactly the stored u.
+#pragma unroll
+        for (int i = 0; i < 8; ++i) w[i] = gelu_erf(__bfloat162float(__float2bfloat16(v[i])));
+    }
+}
+
+// CLUSTER == 2: the two CTAs of a cluster work on vertically adjacent output tiles (same n-tile),
+// each loads half of the shared B tile and TMA-multicasts it to both, halving B's L2 traffic.
+template <int BLOCK_N, bool A_MN, bool B_MN, int EPI, int CLUSTER>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const GemmArgs g) {
-    using Cfg = GemmCfg<BLOCK_N>;
+               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2,
+               const __grid_constant__ CUtensorMap tmR, const GemmArgs g) {
+    using Cfg = GemmCfg<BLOCK_N, EPI>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                                ~(uintptr_t)1023);
     uint8_t* sA = smem;
-    uint8_t* sB = smem + STAGES * Cfg::A_BYTES;
-    uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * Cfg::B_BYTES);
+    uint8_t* sB = sA + STAGES * Cfg::A_BYTES;
+    uint8_t* sR = sB + STAGES * Cfg::B_BYTES;
+    uint8_t* sStg = sR + Cfg::R_BYTES;
+    float* sBias = reinterpret_cast<float*>(sStg + Cfg::STG_BYTES);
+    uint64_t* full = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sBias) + Cfg::BIAS_BYTES);
     uint64_t* empty = full + STAGES;
     uint64_t* tfull = empty + STAGES;
     uint64_t* tempty = tfull + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    uint64_t* rfull = tempty + 2;
+    uint64_t* rempty = rfull + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rempty + 1);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) DBG_STAMP(0);
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
+        tma_prefetch_desc(&tmC);
+        if (Cfg::DUAL) tma_prefetch_desc(&tmC2);
+        if (Cfg::HAS_R) tma_prefetch_desc(&tmR);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], 1);
+            mbar_init(&empty[s], CLUSTER);  // every CTA that multicasts into this stage must be done
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tfull[a], 1);
-            mbar_init(&tempty[a], 4);
+            mbar_init(&tempty[a], EPI_WARPS);
         }
+        mbar_init(rfull, 1);
+        mbar_init(rempty, EPI_WARPS);
         fence_mbar_init();
     }
     if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
     tc_fence_before();
-    __syncthreads();
+    if (CLUSTER > 1) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) DBG_STAMP(1);
 
-    const int tiles_mn = g.m_tiles * g.n_tiles;
+    // work units: (m-tile group of CLUSTER tiles, n-tile, k-split); a cluster walks units together
+    const int cta_rank = CLUSTER > 1 ? (int)cluster_ctarank() : 0;
+    const int m_groups = (g.m_tiles + CLUSTER - 1) / CLUSTER;
+    const int tiles_mn = m_groups * g.n_tiles;
     const int total_tiles = tiles_mn * g.splits;
+    const int unit0 = blockIdx.x / CLUSTER;
+    const int unit_stride = gridDim.x / CLUSTER;
+    constexpr uint16_t MC_MASK = (uint16_t)((1u << CLUSTER) - 1);
 
     if (warp == 0) {
         // ================= TMA producer =================
         if (lane == 0) {
             int s = 0;
-            uint32_t ph = 0;
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            uint32_t ph = 0, rph = 0;
+            for (int t = unit0; t < total_tiles; t += unit_stride) {
                 const int split = t / tiles_mn;
                 const int rem = t - split * tiles_mn;
-                const int m0 = (rem % g.m_tiles) * BLOCK_M;
-                const int n0 = (rem / g.m_tiles) * BLOCK_N;
+                const int m0 = ((rem % m_groups) * CLUSTER + cta_rank) * BLOCK_M;
+                const int n0 = (rem / m_groups) * BLOCK_N;
                 const int kb0 = split * g.kb_per_split;
                 const int kb1 = min(g.num_kb, kb0 + g.kb_per_split);
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&empty[s], ph ^ 1);
-                    mbar_arrive_expect_tx(&full[s], Cfg::A_BYTES + Cfg::B_BYTES);
+                    if (g.dbg_mode == 2) mbar_arrive(&full[s]);
+                    else mbar_arrive_expect_tx(&full[s], Cfg::STAGE_BYTES);
                     uint8_t* a_dst = sA + s * Cfg::A_BYTES;
                     uint8_t* b_dst = sB + s * Cfg::B_BYTES;
-                    if (!A_MN) {
+                    if (g.dbg_mode == 2) {
+                        // bring-up: no operand traffic, the MMAs run on whatever is in smem
+                    } else if (!A_MN) {
                         tma_load_2d(a_dst, &tmA, &full[s], kb * BLOCK_K, m0);
                     } else {
 #pragma unroll
@@ -253,50 +348,93 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             tma_load_2d(a_dst + i * (BLOCK_K * 128), &tmA, &full[s], m0 + 64 * i,
                                         kb * BLOCK_K);
                     }
-                    if (!B_MN) {
-                        tma_load_2d(b_dst, &tmB, &full[s], kb * BLOCK_K, n0);
-                    } else {
+                    if (g.dbg_mode == 2) {
+                    } else if (CLUSTER == 1) {
+                        if (!B_MN) {
+                            tma_load_2d(b_dst, &tmB, &full[s], kb * BLOCK_K, n0);
+                        } else {
 #pragma unroll
-                        for (int i = 0; i < BLOCK_N / 64; ++i)
-                            tma_load_2d(b_dst + i * (BLOCK_K * 128), &tmB, &full[s], n0 + 64 * i,
-                                        kb * BLOCK_K);
+                            for (int i = 0; i < BLOCK_N / 64; ++i)
+                                tma_load_2d(b_dst + i * (BLOCK_K * 128), &tmB, &full[s], n0 + 64 * i,
+                                            kb * BLOCK_K);
+                        }
+                    } else {
+                        // this CTA fetches its 1/CLUSTER slice of the B tile and multicasts it
+                        if (!B_MN) {
+                            constexpr int ROWS = BLOCK_N / CLUSTER;
+                            tma_load_2d_mc(b_dst + cta_rank * (ROWS * 128), &tmB, &full[s], kb * BLOCK_K,
+                                           n0 + cta_rank * ROWS, MC_MASK);
+                        } else {
+                            constexpr int BOXES = BLOCK_N / 64 / CLUSTER;
+#pragma unroll
+                            for (int j = 0; j < BOXES; ++j) {
+                                const int i = cta_rank * BOXES + j;
+                                tma_load_2d_mc(b_dst + i * (BLOCK_K * 128), &tmB, &full[s], n0 + 64 * i,
+                                               kb * BLOCK_K, MC_MASK);
+                            }
+                        }
                     }
                     if (++s == STAGES) { s = 0; ph ^= 1; }
+                    if (Cfg::HAS_R && kb == kb0) {
+                        // side-input tile (residual / pre-activation) for this tile's epilogue
+                        mbar_wait(rempty, rph ^ 1);
+                        mbar_arrive_expect_tx(rfull, Cfg::R_BYTES);
+#pragma unroll
+                        for (int i = 0; i < BLOCK_N / 64; ++i)
+                            tma_load_2d(sR + i * (BLOCK_M * 128), &tmR, rfull, n0 + 64 * i, m0);
+                        rph ^= 1;
+                    }
                 }
             }
+            DBG_STAMP(2);
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
+        // Everything the issuing lane touches is kept warp-uniform (tile/stage counters, smem and
+        // TMEM addresses broadcast with shfl) and the two smem descriptors are built once per stage
+        // and advanced by adding a constant, so the SASS between consecutive UTCHMMAs is a couple of
+        // uniform-datapath adds instead of a per-MMA descriptor rebuild + R2UR waterfall.
         constexpr uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N, A_MN, B_MN);
+        constexpr uint64_t A_TMPL = desc_template(A_MN ? BLOCK_K * 128 : 16, 1024);
+        constexpr uint64_t B_TMPL = desc_template(B_MN ? BLOCK_K * 128 : 16, 1024);
+        constexpr uint64_t A_STEP = (A_MN ? UMMA_K * 128 : UMMA_K * 2) >> 4;
+        constexpr uint64_t B_STEP = (B_MN ? UMMA_K * 128 : UMMA_K * 2) >> 4;
+        const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+        const uint32_t a_base = __shfl_sync(0xffffffffu, smem_u32(sA), 0);
+        const uint32_t b_base = __shfl_sync(0xffffffffu, smem_u32(sB), 0);
+        const bool leader = elect_one();
         int s = 0;
         uint32_t ph = 0;
         int as = 0;
         uint32_t aph = 0;
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        for (int t = unit0; t < total_tiles; t += unit_stride) {
             const int split = t / tiles_mn;
             const int kb0 = split * g.kb_per_split;
             const int kb1 = min(g.num_kb, kb0 + g.kb_per_split);
             mbar_wait(&tempty[as], aph ^ 1);
             tc_fence_after();
-            const uint32_t tmem_d = tmem_base + as * BLOCK_N;
+            const uint32_t tmem_d = tmem_u + as * BLOCK_N;
             for (int kb = kb0; kb < kb1; ++kb) {
                 mbar_wait(&full[s], ph);
                 tc_fence_after();
-                if (lane == 0) {
-                    const uint32_t a_addr = smem_u32(sA + s * Cfg::A_BYTES);
-                    const uint32_t b_addr = smem_u32(sB + s * Cfg::B_BYTES);
+                if (lane == 0 && kb == kb0 && t == unit0) DBG_STAMP(3);
+                if (leader) {
+                    if (g.dbg_mode != 1) {
+                        const uint64_t ad = A_TMPL | (uint64_t)(((a_base + s * Cfg::A_BYTES) >> 4) & 0x3FFF);
+                        const uint64_t bd = B_TMPL | (uint64_t)(((b_base + s * Cfg::B_BYTES) >> 4) & 0x3FFF);
+                        umma_bf16(tmem_d, ad, bd, idesc, kb > kb0 ? 1u : 0u);
 #pragma unroll
-                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                        const uint64_t ad =
-                            A_MN ? make_smem_desc(a_addr + k * (UMMA_K * 128), BLOCK_K * 128, 1024)
-                                 : make_smem_desc(a_addr + k * (UMMA_K * 2), 16, 1024);
-                        const uint64_t bd =
-                            B_MN ? make_smem_desc(b_addr + k * (UMMA_K * 128), BLOCK_K * 128, 1024)
-                                 : make_smem_desc(b_addr + k * (UMMA_K * 2), 16, 1024);
-                        umma_bf16(tmem_d, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                        for (int k = 1; k < BLOCK_K / UMMA_K; ++k)
+                            umma_bf16(tmem_d, ad + k * A_STEP, bd + k * B_STEP, idesc, 1u);
                     }
-                    umma_commit(&empty[s]);
-                    if (kb == kb1 - 1) umma_commit(&tfull[as]);
+                    if (g.dbg_mode == 1) {
+                        mbar_arrive(&empty[s]);  // TMA-only bring-up mode (CLUSTER == 1 only)
+                        if (kb == kb1 - 1) mbar_arrive(&tfull[as]);
+                    } else {
+                        if (CLUSTER == 1) umma_commit(&empty[s]);
+                        else umma_commit_mc(&empty[s], MC_MASK);
+                        if (kb == kb1 - 1) umma_commit(&tfull[as]);
+                    }
                 }
                 __syncwarp();
                 if (++s == STAGES) { s = 0; ph ^= 1; }
@@ -304,45 +442,123 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             as ^= 1;
             if (as == 0) aph ^= 1;
         }
+        if (lane == 0) DBG_STAMP(4);
     } else if (warp >= 4) {
-        // ================= epilogue =================
-        const int q = warp & 3;  // TMEM lane quadrant this warp may access
+        // ================= epilogue: TMEM -> regs -> fused math -> swizzled smem -> TMA store =========
+        const int ew = warp - 4;
+        const int q = warp & 3;    // TMEM lane quadrant this warp may access
+        const int half = ew >> 2;  // the two warps of a quadrant alternate over column groups
+        uint8_t* stg = sStg + ew * Cfg::STG_PER_WARP;
+        float* bias_s = sBias + ew * BLOCK_N;
         const uint64_t seed = (EPI == B200U_EPI_BIAS_DROP_RES) ? load_seed(g.drop) : 0ull;
+        const int rr = q * 32 + lane;  // row inside the tile
+        const int sw = lane & 7;       // 128B-swizzle phase of this row
         int as = 0;
-        uint32_t aph = 0;
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        uint32_t aph = 0, rph = 0;
+        for (int t = unit0; t < total_tiles; t += unit_stride) {
             const int split = t / tiles_mn;
             const int rem = t - split * tiles_mn;
-            const int m0 = (rem % g.m_tiles) * BLOCK_M;
-            const int n0 = (rem / g.m_tiles) * BLOCK_N;
+            const int m0 = ((rem % m_groups) * CLUSTER + cta_rank) * BLOCK_M;
+            const int n0 = (rem / m_groups) * BLOCK_N;
+            if (Cfg::HAS_BIAS) {
+                // bias slice of this tile -> per-warp smem while the main loop is still running
+                for (int c = lane; c < BLOCK_N; c += 32)
+                    bias_s[c] = (g.bias && n0 + c < g.N) ? g.bias[n0 + c] : 0.f;
+                __syncwarp();
+            }
             mbar_wait(&tfull[as], aph);
             tc_fence_after();
-            const int row = m0 + q * 32 + lane;
+            if (threadIdx.x == 128 && t == unit0) DBG_STAMP(5);
+            if (Cfg::HAS_R) mbar_wait(rfull, rph);
+            const int row = m0 + rr;
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BLOCK_N;
 #pragma unroll 1
-            for (int c = 0; c < BLOCK_N / 32; ++c) {
-                uint32_t r[32];
-                tmem_ld_32x32(taddr + c * 32, r);
-                tmem_ld_wait();
-                float acc[32];
+            for (int gi = half; gi < Cfg::NUM_GROUPS; gi += 2) {
+                const int col0 = gi * Cfg::GROUP_COLS;
+                if (n0 + col0 >= g.N) break;  // whole group outside the matrix (uniform)
+                if (Cfg::F32_OUT) {
+                    uint32_t r[32];
+                    tmem_ld_32x32(taddr + col0, r);
+                    tmem_ld_wait();
+                    if (lane == 0) bulk_wait_read_all();  // staging buffer free again?
+                    __syncwarp();
 #pragma unroll
-                for (int i = 0; i < 32; ++i) acc[i] = __uint_as_float(r[i]);
-                epilogue_row32<EPI>(acc, row, n0 + c * 32, g, seed);
+                    for (int j = 0; j < 8; ++j) {
+                        float4 o;
+                        o.x = __uint_as_float(r[4 * j + 0]); o.y = __uint_as_float(r[4 * j + 1]);
+                        o.z = __uint_as_float(r[4 * j + 2]); o.w = __uint_as_float(r[4 * j + 3]);
+                        if (EPI == B200U_EPI_STORE_F32) {
+                            o.x += bias_s[col0 + 4 * j + 0]; o.y += bias_s[col0 + 4 * j + 1];
+                            o.z += bias_s[col0 + 4 * j + 2]; o.w += bias_s[col0 + 4 * j + 3];
+                        }
+                        *reinterpret_cast<float4*>(stg + lane * 128 + ((j ^ sw) << 4)) = o;
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (EPI == B200U_EPI_ATOMIC_F32) tma_reduce_add_2d(&tmC, stg, n0 + col0, m0 + q * 32);
+                        else tma_store_2d(&tmC, stg, n0 + col0, m0 + q * 32);
+                        bulk_commit();
+                    }
+                } else {
+                    uint32_t r0[32], r1[32];
+                    tmem_ld_32x32(taddr + col0, r0);
+                    tmem_ld_32x32(taddr + col0 + 32, r1);
+                    tmem_ld_wait();
+                    if (lane == 0) bulk_wait_read_all();
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float v[8], w[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            v[i] = __uint_as_float(j < 4 ? r0[8 * j + i] : r1[8 * (j - 4) + i]);
+                        uint4 rraw = make_uint4(0, 0, 0, 0);
+                        if (Cfg::HAS_R)
+                            rraw = *reinterpret_cast<const uint4*>(sR + gi * (BLOCK_M * 128) + rr * 128 + ((j ^ sw) << 4));
+                        epi_math8<EPI>(v, w, bias_s + col0 + 8 * j, rraw, g, seed, row, n0 + col0 + 8 * j);
+                        uint4 o;
+                        o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]);
+                        o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
+                        *reinterpret_cast<uint4*>(stg + lane * 128 + ((j ^ sw) << 4)) = o;
+                        if (Cfg::DUAL) {
+                            uint4 o2;
+                            o2.x = pack_bf16(w[0], w[1]); o2.y = pack_bf16(w[2], w[3]);
+                            o2.z = pack_bf16(w[4], w[5]); o2.w = pack_bf16(w[6], w[7]);
+                            *reinterpret_cast<uint4*>(stg + 4096 + lane * 128 + ((j ^ sw) << 4)) = o2;
+                        }
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(&tmC, stg, n0 + col0, m0 + q * 32);
+                        if (Cfg::DUAL) tma_store_2d(&tmC2, stg + 4096, n0 + col0, m0 + q * 32);
+                        bulk_commit();
+                    }
+                }
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[as]);
+            if (lane == 0) {
+                mbar_arrive(&tempty[as]);
+                if (Cfg::HAS_R) mbar_arrive(rempty);
+            }
+            rph ^= 1;
             as ^= 1;
             if (as == 0) aph ^= 1;
         }
+        if (lane == 0) bulk_wait_all();  // all TMA stores of this warp have landed
+        if (threadIdx.x == 128) DBG_STAMP(6);
     }
 
     tc_fence_before();
-    __syncthreads();
+    // no CTA may exit while its peer can still multicast into its smem or arrive on its barriers
+    if (CLUSTER > 1) cluster_sync_all(); else __syncthreads();
     if (warp == 2) {
         tc_fence_after();
         tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
     }
+    if (threadIdx.x == 0) DBG_STAMP(7);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -378,6 +594,9 @@ __global__ void gemm_simt_kernel(const bf16* __restrict__ A, int lda, int a_mn,
 // ---------------------------------------------------------------------------------------
 // Host side
 // ---------------------------------------------------------------------------------------
+static long long* g_dbg_ptr = nullptr;
+static int g_dbg_mode = 0;
+
 static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
     static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
     if (!fn) {
@@ -391,46 +610,57 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
     return fn;
 }
 
-// bf16 matrix stored as [rows, cols] row-major with leading dimension ld; box = 64 cols x box_rows.
-static int make_tmap(CUtensorMap* tm, const void* ptr, int rows, int cols, int ld, int box_rows) {
+// matrix stored as [rows, cols] row-major with leading dimension ld (elements); box = box_cols x
+// box_rows with a 128-byte swizzled inner dimension (64 bf16 or 32 f32 columns).
+static int make_tmap(CUtensorMap* tm, const void* ptr, int rows, int cols, int ld, int box_rows,
+                     bool f32 = false) {
     auto fn = get_encode_fn();
     if (!fn) {
         set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
         return B200U_ERR_CUDA;
     }
+    const int esz = f32 ? 4 : 2;
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-    cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * esz};
+    cuuint32_t box[2] = {(cuuint32_t)(128 / esz), (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1u, 1u};
-    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides,
-                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = fn(tm, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                    const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
-        set_error("cuTensorMapEncodeTiled failed (%d) ptr=%p rows=%d cols=%d ld=%d box_rows=%d", (int)r,
-                  ptr, rows, cols, ld, box_rows);
+        set_error("cuTensorMapEncodeTiled failed (%d) ptr=%p rows=%d cols=%d ld=%d box_rows=%d f32=%d",
+                  (int)r, ptr, rows, cols, ld, box_rows, (int)f32);
         return B200U_ERR_CUDA;
     }
     return B200U_OK;
 }
 
-template <int BLOCK_N, bool A_MN, bool B_MN, int EPI>
+template <int BLOCK_N, bool A_MN, bool B_MN, int EPI, int CLUSTER>
 static int launch_tc(const b200u_gemm_t* d, GemmArgs& g, cudaStream_t stream) {
-    using Cfg = GemmCfg<BLOCK_N>;
-    CUtensorMap tmA, tmB;
+    using Cfg = GemmCfg<BLOCK_N, EPI>;
+    CUtensorMap tmA, tmB, tmC, tmC2, tmR;
     int rc;
     if (!A_MN) rc = make_tmap(&tmA, d->A, d->M, d->K, d->lda, BLOCK_M);
     else       rc = make_tmap(&tmA, d->A, d->K, d->M, d->lda, BLOCK_K);
     if (rc) return rc;
-    if (!B_MN) rc = make_tmap(&tmB, d->B, d->N, d->K, d->ldb, BLOCK_N);
+    if (!B_MN) rc = make_tmap(&tmB, d->B, d->N, d->K, d->ldb, BLOCK_N / CLUSTER);
     else       rc = make_tmap(&tmB, d->B, d->K, d->N, d->ldb, BLOCK_K);
     if (rc) return rc;
+    rc = make_tmap(&tmC, d->C, d->M, d->N, d->ldc, 32, Cfg::F32_OUT);
+    if (rc) return rc;
+    tmC2 = tmC;
+    tmR = tmC;
+    if (Cfg::DUAL) { rc = make_tmap(&tmC2, d->C2, d->M, d->N, d->ldc2, 32); if (rc) return rc; }
+    if (Cfg::HAS_R) { rc = make_tmap(&tmR, d->R, d->M, d->N, d->ldr, BLOCK_M); if (rc) return rc; }
 
     g.m_tiles = (d->M + BLOCK_M - 1) / BLOCK_M;
     g.n_tiles = (d->N + BLOCK_N - 1) / BLOCK_N;
-    const int total = g.m_tiles * g.n_tiles * g.splits;
-    const int grid = total < num_sms() ? total : num_sms();
+    const int units = ((g.m_tiles + CLUSTER - 1) / CLUSTER) * g.n_tiles * g.splits;
+    const int max_clusters = num_sms() / CLUSTER;
+    const int grid = (units < max_clusters ? units : max_clusters) * CLUSTER;
 
-    auto kern = gemm_tc_kernel<BLOCK_N, A_MN, B_MN, EPI>;
+    auto kern = gemm_tc_kernel<BLOCK_N, A_MN, B_MN, EPI, CLUSTER>;
     static bool attr_set = false;  // per template instantiation
     if (!attr_set) {
         B200U_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -439,18 +669,30 @@ static int launch_tc(const b200u_gemm_t* d, GemmArgs& g, cudaStream_t stream) {
     }
     int slot = 0;
     const bool prof = prof_begin(stream, 2.0 * d->M * d->N * d->K, &slot);
-    kern<<<grid, 256, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, g);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CLUSTER;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    B200U_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, tmC2, tmR, g));
     if (prof) prof_end(stream, slot);
     B200U_CHECK_LAUNCH("gemm_tc_kernel");
     return B200U_OK;
 }
 
-template <int BLOCK_N, int EPI>
+template <int BLOCK_N, int EPI, int CLUSTER>
 static int dispatch_major(const b200u_gemm_t* d, GemmArgs& g, cudaStream_t stream) {
-    if (!d->a_mn_major && !d->b_mn_major) return launch_tc<BLOCK_N, false, false, EPI>(d, g, stream);
-    if (!d->a_mn_major && d->b_mn_major) return launch_tc<BLOCK_N, false, true, EPI>(d, g, stream);
-    if (d->a_mn_major && d->b_mn_major) return launch_tc<BLOCK_N, true, true, EPI>(d, g, stream);
-    return launch_tc<BLOCK_N, true, false, EPI>(d, g, stream);
+    if (!d->a_mn_major && !d->b_mn_major) return launch_tc<BLOCK_N, false, false, EPI, CLUSTER>(d, g, stream);
+    if (!d->a_mn_major && d->b_mn_major) return launch_tc<BLOCK_N, false, true, EPI, CLUSTER>(d, g, stream);
+    if (d->a_mn_major && d->b_mn_major) return launch_tc<BLOCK_N, true, true, EPI, CLUSTER>(d, g, stream);
+    return launch_tc<BLOCK_N, true, false, EPI, CLUSTER>(d, g, stream);
 }
 
 template <int EPI>
@@ -463,13 +705,29 @@ static int dispatch_bn(const b200u_gemm_t* d, GemmArgs& g, int block_n, cudaStre
         B200U_CHECK_LAUNCH("gemm_simt_kernel");
         return B200U_OK;
     }
-    if (block_n == 256) return dispatch_major<256, EPI>(d, g, stream);
-    return dispatch_major<128, EPI>(d, g, stream);
+    // pairs of vertically adjacent tiles share their B tile through TMA multicast
+    // (measured on B200: multicast at cluster size 2 does not reduce per-SM ingest, so auto = off)
+    const bool pair = d->cluster == 2;
+    if (pair) {
+        if (block_n == 256) return dispatch_major<256, EPI, 2>(d, g, stream);
+        return dispatch_major<128, EPI, 2>(d, g, stream);
+    }
+    if (block_n == 256) return dispatch_major<256, EPI, 1>(d, g, stream);
+    return dispatch_major<128, EPI, 1>(d, g, stream);
 }
 
 }  // namespace b200u
 
 using namespace b200u;
+
+// Bring-up aid: when set, every tcgen05 GEMM CTA writes 8 clock64() phase stamps to ptr[cta*8..].
+extern "C" int b200u_gemm_debug_stamps(long long* device_ptr) {
+    // low 2 bits of the (8-byte aligned) pointer select a bring-up mode: 1 = TMA-only, 2 = MMA-only
+    g_dbg_mode = (int)((uintptr_t)device_ptr & 3);
+    device_ptr = (long long*)((uintptr_t)device_ptr & ~(uintptr_t)3);
+    g_dbg_ptr = device_ptr;
+    return B200U_OK;
+}
 
 extern "C" int b200u_gemm(const b200u_gemm_t* d, b200u_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
@@ -485,7 +743,7 @@ extern "C" int b200u_gemm(const b200u_gemm_t* d, b200u_stream_t stream_) {
                         ((uintptr_t)d->C & 15) == 0,
                     "b200u_gemm: operands must be 16-byte aligned");
     const bool f32_out = d->epilogue == B200U_EPI_ATOMIC_F32 || d->epilogue == B200U_EPI_STORE_F32;
-    B200U_CHECK_ARG(d->ldc % (f32_out ? 4 : 8) == 0 || d->N < 8,
+    B200U_CHECK_ARG(d->ldc % (f32_out ? 4 : 8) == 0,
                     "b200u_gemm: ldc alignment (got %d)", d->ldc);
     if (d->epilogue == B200U_EPI_BIAS_GELU)
         B200U_CHECK_ARG(d->C2 && d->bias && d->ldc2 % 8 == 0, "b200u_gemm: BIAS_GELU needs C2 and bias");
@@ -518,6 +776,10 @@ extern "C" int b200u_gemm(const b200u_gemm_t* d, b200u_stream_t stream_) {
         const int t256 = m_tiles * ((d->N + 255) / 256);
         block_n = (d->N >= 256 && t256 >= num_sms()) ? 256 : 128;
     }
+    // epilogues that stage a side-input tile in smem keep 128-wide tiles (>= 4 pipeline stages)
+    if (d->block_n == 0 && (d->epilogue == B200U_EPI_BIAS_DROP_RES || d->epilogue == B200U_EPI_ADD ||
+                            d->epilogue == B200U_EPI_DGELU))
+        block_n = 128;
     int splits = d->splits;
     if (d->epilogue != B200U_EPI_ATOMIC_F32) splits = 1;
     else if (splits <= 0) {
@@ -530,6 +792,8 @@ extern "C" int b200u_gemm(const b200u_gemm_t* d, b200u_stream_t stream_) {
     g.splits = (g.num_kb + g.kb_per_split - 1) / g.kb_per_split;
     g.m_tiles = m_tiles;
     g.n_tiles = 0;
+    g.dbg = g_dbg_ptr;
+    g.dbg_mode = g_dbg_mode;
 
     switch (d->epilogue) {
         case B200U_EPI_STORE:         return dispatch_bn<B200U_EPI_STORE>(d, g, block_n, stream);

@@ -18,7 +18,7 @@ def _ld(t):
 
 
 def gemm(a, b, *, a_mn=False, b_mn=False, epilogue=EPI_STORE, out=None, out2=None, bias=None,
-         res=None, drop=None, splits=0, block_n=0, impl=0):
+         res=None, drop=None, splits=0, block_n=0, impl=0, cluster=0):
     """acc[M,N] = sum_k A(m,k) B(n,k) with a fused epilogue (see include/b200u.h, K3).
 
     a: [M,K] (or [K,M] when a_mn), b: [N,K] (or [K,N] when b_mn); bf16, row-major.
@@ -50,7 +50,7 @@ def gemm(a, b, *, a_mn=False, b_mn=False, epilogue=EPI_STORE, out=None, out2=Non
         g.R, g.ldr = res.data_ptr(), _ld(res)
     if drop is not None:
         g.drop = drop
-    g.splits, g.block_n, g.impl = splits, block_n, impl
+    g.splits, g.block_n, g.impl, g.cluster = splits, block_n, impl, cluster
     _lib.check(_lib.lib().b200u_gemm(C.byref(g), _lib.stream_ptr()), "b200u_gemm")
     return (out, out2) if epilogue == EPI_BIAS_GELU else out
 
