@@ -109,6 +109,9 @@ int b200u_layernorm_bwd(const void* dy, const void* x, int x_dtype, const float*
 
 /* out[n] += sum_m x[m,n] (bf16 in, f32 accumulate): nn.Linear bias gradients. */
 int b200u_colsum_accum(const void* x, int ldx, float* out, int M, int N, b200u_stream_t stream);
+/* out = dy * gelu_erf'(u), bf16, n % 8 == 0 (backward of dense+GELU head transforms,
+ * model/layer.py:196-200, model/pretrain.py:23-25). */
+int b200u_dgelu_mul(const void* dy, const void* u, void* out, size_t n, b200u_stream_t stream);
 /* y(bf16)[i] = x(f32)[i], n % 8 == 0: img_feat / weight shadow casts. */
 int b200u_cast_f32_to_bf16(const float* x, void* y, size_t n, b200u_stream_t stream);
 
@@ -228,6 +231,26 @@ int b200u_linear_small_bwd(const float* dout, const float* x, const float* W, fl
  * Any of loss/dlogits/probs may be NULL. */
 int b200u_bce_logits(const float* logits, const float* labels, float pos_weight, float grad_scale,
                      float* loss, float* dlogits, float* probs, int B, b200u_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K8  optimal transport (model/ot.py), fp32. x [B,M,D] text, y [B,N,D] regions, pads uint8
+ * (1 = padding) [B,M] / [B,N].
+ *  cosine_cost : cost[B,M,N] = 1 - normalize(x)·normalize(y)ᵀ with joint padding zeroed
+ *                (ot.py:11-21,72-75); xinv/yinv = 1/max(norm, eps) are kept for the backward.
+ *  ipot        : T[B,N,M] after `iterations` IPOT steps, one launch (ot.py:35-66).
+ *  ot_distance : dist[B] = trace(cost · T) (ot.py:24-32,84).
+ *  cosine_cost_bwd : d dist / d x, d y with T detached (ot.py:82-84). */
+int b200u_cosine_cost(const float* x, const float* y, const unsigned char* x_pad,
+                      const unsigned char* y_pad, float* cost, float* xinv, float* yinv, int B, int M,
+                      int N, int D, float eps, b200u_stream_t stream);
+int b200u_ipot(const float* cost, const unsigned char* x_pad, const unsigned char* y_pad, float* T,
+               int B, int M, int N, float beta, int iterations, int k, b200u_stream_t stream);
+int b200u_ot_distance(const float* cost, const float* T, float* dist, int B, int M, int N,
+                      b200u_stream_t stream);
+int b200u_cosine_cost_bwd(const float* x, const float* y, const float* xinv, const float* yinv,
+                          const unsigned char* x_pad, const unsigned char* y_pad, const float* T,
+                          const float* ddist, float* dx, float* dy, int B, int M, int N, int D,
+                          b200u_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * K10 fused optimizer step over flat f32 buffers (train_template.py:89-107,

@@ -25,6 +25,7 @@ SIGNATURES = {
     "b200u_layernorm_fwd": (_i, [_p, _i, _p, _p, _p, _i, _p, _p, _i, _i, _f, _p, _p]),
     "b200u_layernorm_bwd": (_i, [_p, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p, _i, _p]),
     "b200u_colsum_accum": (_i, [_p, _i, _p, _i, _i, _p]),
+    "b200u_dgelu_mul": (_i, [_p, _p, _p, _sz, _p]),
     "b200u_cast_f32_to_bf16": (_i, [_p, _p, _sz, _p]),
     "b200u_gather_rows": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
     "b200u_gather_rows_bwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
@@ -41,6 +42,10 @@ SIGNATURES = {
     "b200u_linear_small_fwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _p]),
     "b200u_linear_small_bwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _p]),
     "b200u_bce_logits": (_i, [_p, _p, _f, _f, _p, _p, _p, _i, _p]),
+    "b200u_cosine_cost": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _p]),
+    "b200u_ipot": (_i, [_p, _p, _p, _p, _i, _i, _i, _f, _i, _i, _p]),
+    "b200u_ot_distance": (_i, [_p, _p, _p, _i, _i, _i, _p]),
+    "b200u_cosine_cost_bwd": (_i, [_p] * 10 + [_i, _i, _i, _i, _p]),
     "b200u_counter_add": (_i, [_p, _ull, _p]),
     "b200u_grad_sumsq": (_i, [_p, _sz, _p, _p]),
     "b200u_clip_coef": (_i, [_p, _f, _f, _p, _p, _p]),

@@ -270,6 +270,20 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ x, bf16* __restri
     }
 }
 
+// out = dy * gelu_erf'(u)  (backward of the standalone dense+GELU transforms of the heads)
+__global__ void dgelu_mul_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ u,
+                                 bf16* __restrict__ out, size_t nvec) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nvec;
+         i += (size_t)gridDim.x * blockDim.x) {
+        float a[8], b[8];
+        load8(dy + i * 8, a);
+        load8(u + i * 8, b);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] *= gelu_erf_grad(b[j]);
+        store8(out + i * 8, a);
+    }
+}
+
 // ---------------------------------------------------------------------------------------
 // K1 gather: out[b, j, :] = (idx < T ? txt[b, idx] : img[b, idx - T]),  idx = gather_index[b, j]
 // Pure 16-byte row copies -> bit-exact with torch.gather on the concatenation, padded
@@ -423,6 +437,19 @@ extern "C" int b200u_cast_f32_to_bf16(const float* x, void* y, size_t n, b200u_s
     if (grid > cap) grid = cap;
     cast_f32_bf16_kernel<<<(int)grid, 256, 0, stream>>>(x, (bf16*)y, nvec);
     B200U_CHECK_LAUNCH("cast_f32_to_bf16");
+    return B200U_OK;
+}
+
+extern "C" int b200u_dgelu_mul(const void* dy, const void* u, void* out, size_t n, b200u_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    B200U_CHECK_ARG(dy && u && out && n % 8 == 0, "dgelu_mul: n must be a multiple of 8");
+    if (n == 0) return B200U_OK;
+    const size_t nvec = n / 8;
+    size_t grid = (nvec + 255) / 256;
+    const size_t cap = (size_t)num_sms() * 16;
+    if (grid > cap) grid = cap;
+    dgelu_mul_kernel<<<(int)grid, 256, 0, stream>>>((const bf16*)dy, (const bf16*)u, (bf16*)out, nvec);
+    B200U_CHECK_LAUNCH("dgelu_mul");
     return B200U_OK;
 }
 

@@ -17,7 +17,19 @@ import torch
 
 from . import _lib, ops
 
+import weakref
+
 ALIGN = 8  # elements: keeps every tensor 32-byte (fp32) / 16-byte (bf16) aligned
+
+_STORE_OF = {}  # id(param) -> weakref(FlatStore) for parameters that live in a flat store
+
+
+def store_of(p):
+    ref = _STORE_OF.get(id(p))
+    st = ref() if ref is not None else None
+    if st is not None and st.flat is not None and id(p) in st.index and st.valid():
+        return st
+    return None
 
 
 def _ordered_params(root):
@@ -103,6 +115,7 @@ class FlatStore(object):
                 p.grad = gview
                 self.entries.append((name, p, off, n))
                 self.index[id(p)] = (off, n)
+                _STORE_OF[id(p)] = weakref.ref(self)
         self.flat, self.grad = flat, grad
         self.shadow = torch.empty(total, device=dev, dtype=torch.bfloat16)
         self._shadow_version = None

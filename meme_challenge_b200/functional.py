@@ -456,3 +456,100 @@ def bce_with_logits(logits, labels, pos_weight=1.0, grad_scale=1.0, want_grad=Tr
     probs = torch.empty(B, device=x.device, dtype=torch.float32)
     ops._call("b200u_bce_logits", P(x), P(y), float(pos_weight), float(grad_scale), P(loss), P(dl), P(probs), B)
     return loss, dl, probs
+
+
+# ------------------------------------------------------------------------------------------------
+# Generic nn.Linear on the tcgen05 GEMM (pretraining heads: model/layer.py:188-233,
+# model/pretrain.py:19-47). Weight shadows come from the owning FlatStore when there is one (tied
+# weights: word_embeddings / img_linear), else from a small per-parameter cache.
+# ------------------------------------------------------------------------------------------------
+_shadow_cache = {}
+
+
+def shadow_for(p):
+    from .flat import store_of
+    st = store_of(p)
+    if st is not None:
+        st.refresh_shadow()
+        return st.w16(p)
+    key = id(p)
+    hit = _shadow_cache.get(key)
+    if hit is None or hit[0] != p._version or hit[1] != p.data_ptr():
+        w16 = torch.empty(p.shape, device=p.device, dtype=torch.bfloat16)
+        ops.cast_f32_to_bf16(p.detach().contiguous().view(-1), w16.view(-1))
+        hit = (p._version, p.data_ptr(), w16)
+        _shadow_cache[key] = hit
+    return hit[2]
+
+
+def _pad8(n):
+    return (n + 7) // 8 * 8
+
+
+class LinearFn(torch.autograd.Function):
+    """y = x·Wᵀ + b (or x·W + b when `transposed`, model/pretrain.py:31) with optional fused GELU.
+    x bf16 [n, K]; y bf16, or fp32 when out_f32 (logits)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, transposed, gelu, out_f32):
+        assert x.dim() == 2
+        x = x.to(torch.bfloat16).contiguous()
+        n, K = x.shape
+        w16 = shadow_for(weight)
+        N = weight.shape[1] if transposed else weight.shape[0]
+        ld = _pad8(N)
+        if n == 0:
+            ctx.empty = True
+            ctx.shape = (n, K)
+            return torch.zeros(0, N, device=x.device, dtype=torch.float32 if out_f32 else torch.bfloat16)
+        ctx.empty = False
+        u = None
+        if gelu:
+            ubuf = torch.empty(n, ld, device=x.device, dtype=torch.bfloat16)
+            gbuf = torch.empty(n, ld, device=x.device, dtype=torch.bfloat16)
+            ops.gemm(x, w16, b_mn=transposed, epilogue=_lib.EPI_BIAS_GELU, out=ubuf[:, :N], out2=gbuf[:, :N],
+                     bias=bias)
+            u, y = ubuf[:, :N], gbuf[:, :N]
+        else:
+            ybuf = torch.empty(n, ld, device=x.device, dtype=torch.float32 if out_f32 else torch.bfloat16)
+            y = ybuf[:, :N]
+            ops.gemm(x, w16, b_mn=transposed, epilogue=EPI_STORE_F32 if out_f32 else _lib.EPI_STORE, out=y,
+                     bias=bias)
+        ctx.save_for_backward(x, u)
+        ctx.params = (weight, bias, w16)
+        ctx.flags = (transposed, gelu)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        if ctx.empty:
+            return torch.zeros(ctx.shape, device=dy.device, dtype=torch.bfloat16), None, None, None, None, None
+        x, u = ctx.saved_tensors
+        weight, bias, w16 = ctx.params
+        transposed, gelu = ctx.flags
+        n, K = x.shape
+        N = dy.shape[1]
+        ld = _pad8(N)
+        dyb = torch.zeros(n, ld, device=dy.device, dtype=torch.bfloat16)
+        dyb[:, :N] = dy  # bf16, 16-byte aligned rows (N may be 28996)
+        dyv = dyb[:, :N]
+        if gelu:
+            # d(pre-activation) = dy * gelu'(u); u lives in a buffer with the same padded stride
+            ubuf = u._base if u._base is not None else u
+            ops._call("b200u_dgelu_mul", P(dyb), P(ubuf), P(dyb), C.c_size_t(dyb.numel()))
+        if bias is not None:
+            ops.colsum_accum(dyb, grad_buf(bias)) if ld == N else grad_buf(bias).add_(dyv.float().sum(0))
+        gw = grad_buf(weight)
+        if transposed:
+            # W [K, N]: dW += xᵀ·dy ; dx = dy·Wᵀ
+            ops.gemm(x, dyv, a_mn=True, b_mn=True, epilogue=EPI_ATOMIC_F32, out=gw)
+            dx = ops.gemm(dyv, w16)
+        else:
+            # W [N, K]: dW += dyᵀ·x ; dx = dy·W
+            ops.gemm(dyv, x, a_mn=True, b_mn=True, epilogue=EPI_ATOMIC_F32, out=gw)
+            dx = ops.gemm(dyv, w16, b_mn=True)
+        return dx, None, None, None, None, None
+
+
+def linear(x, weight, bias=None, transposed=False, gelu=False, out_f32=False):
+    return LinearFn.apply(x, weight, bias, transposed, gelu, out_f32)

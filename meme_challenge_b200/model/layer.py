@@ -114,3 +114,45 @@ class BertPooler(nn.Module):
         if hidden_states.dtype != torch.bfloat16:
             hidden_states = hidden_states.to(torch.bfloat16)
         return F_.PoolerFn.apply(hidden_states.contiguous(), self.dense.weight, self.dense.bias)
+
+
+class BertPredictionHeadTransform(nn.Module):
+    """model/layer.py:188-201: dense -> gelu -> LayerNorm (GELU fused into the GEMM epilogue)."""
+
+    def __init__(self, config):
+        super(BertPredictionHeadTransform, self).__init__()
+        self.dense = nn.Linear(config.hidden_size, config.hidden_size)
+        self.transform_act_fn = ACT2FN[config.hidden_act] if isinstance(config.hidden_act, str) else config.hidden_act
+        self.LayerNorm = BertLayerNorm(config.hidden_size, eps=1e-12)
+
+    def forward(self, hidden_states):
+        hidden_states = F_.linear(hidden_states, self.dense.weight, self.dense.bias, gelu=True)
+        return self.LayerNorm(hidden_states)
+
+
+class BertLMPredictionHead(nn.Module):
+    """model/layer.py:204-221: decoder weight tied to the word embeddings + output-only bias;
+    logits are fp32 [n_masked, vocab]."""
+
+    def __init__(self, config, bert_model_embedding_weights):
+        super(BertLMPredictionHead, self).__init__()
+        self.transform = BertPredictionHeadTransform(config)
+        self.decoder = nn.Linear(bert_model_embedding_weights.size(1), bert_model_embedding_weights.size(0),
+                                 bias=False)
+        self.decoder.weight = bert_model_embedding_weights
+        self.bias = nn.Parameter(torch.zeros(bert_model_embedding_weights.size(0)))
+
+    def forward(self, hidden_states):
+        hidden_states = self.transform(hidden_states)
+        return F_.linear(hidden_states, self.decoder.weight, self.bias, out_f32=True)
+
+
+class BertOnlyMLMHead(nn.Module):
+    """model/layer.py:224-233."""
+
+    def __init__(self, config, bert_model_embedding_weights):
+        super(BertOnlyMLMHead, self).__init__()
+        self.predictions = BertLMPredictionHead(config, bert_model_embedding_weights)
+
+    def forward(self, sequence_output):
+        return self.predictions(sequence_output)

@@ -39,6 +39,7 @@ TINY = dict(vocab_size=120, hidden_size=128, num_hidden_layers=2, num_attention_
             attention_probs_dropout_prob=0.1, max_position_embeddings=64, type_vocab_size=2,
             initializer_range=0.02)
 IMG_DIM = 64
+LABEL_DIM = 24
 
 
 def main():
@@ -108,6 +109,32 @@ def main():
     np.savez_compressed(os.path.join(OUT, "ot.npz"), txt=txt.numpy(), img=img.numpy(),
                         txt_pad=txt_pad.numpy(), img_pad=img_pad.numpy(), cost=cost.numpy(),
                         T=T.numpy(), dist=dist.numpy())
+    # ---- 4. tiny UniterForPretraining: per-task losses (model/pretrain.py), eval mode
+    import model.pretrain as rpre
+    from oracle.uniter_oracle import synth_pretrain_batch
+    torch.manual_seed(1)
+    pm = rpre.UniterForPretraining(cfg, IMG_DIM, LABEL_DIM)
+    with torch.no_grad():
+        for n, p in pm.named_parameters():
+            if "LayerNorm" in n or "layer_norm" in n or n.endswith("bias") or ".net.2." in n:
+                p.add_(torch.randn(p.shape, generator=gen) * 0.05)
+    pm.eval()
+    pb = synth_pretrain_batch(4, 12, 10, seed=21, img_dim=IMG_DIM, vocab=TINY["vocab_size"], label_dim=LABEL_DIM,
+                              min_txt=3, min_bb=2)
+    out = {"sd." + k: v.detach().numpy() for k, v in pm.state_dict().items()}
+    for k, v in pb.items():
+        if torch.is_tensor(v):
+            out["in." + k] = v.numpy()
+    for k, v in pb["ot_inputs"].items():
+        out["ot." + k] = v.numpy() if torch.is_tensor(v) else np.array(v)
+    with torch.no_grad():
+        out["loss.mlm"] = pm(pb, "mlm").numpy()
+        out["loss.mrfr"] = pm(pb, "mrfr").numpy()
+        out["loss.itm"] = pm(pb, "itm").numpy()
+        out["loss.mrc-kl"] = pm(pb, "mrc-kl").numpy()
+        out["loss.mrc"] = pm(pb, "mrc").numpy()
+        out["scores.mlm"] = pm(pb, "mlm", compute_loss=False).numpy()
+    np.savez_compressed(os.path.join(OUT, "tiny_pretrain.npz"), **out)
     print("golden vectors written to", os.path.abspath(OUT))
     for f in sorted(os.listdir(OUT)):
         print("  %-28s %8d bytes" % (f, os.path.getsize(os.path.join(OUT, f))))

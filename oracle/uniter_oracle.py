@@ -287,3 +287,97 @@ def synth_batch(B, T, R, seed=1234, variable=False, img_dim=2048, vocab=28996, m
     labels = (torch.rand(B, generator=g) < 0.36).long()
     return dict(input_ids=input_ids, position_ids=position_ids, img_feat=img_feat, img_pos_feat=pos,
                 attn_mask=attn, gather_index=gi, labels=labels, txt_lens=txt_lens, num_bbs=num_bbs)
+
+
+# ----------------------------------------------------------------------------------------------
+# model/pretrain.py + model/layer.py:188-233 — pretraining heads (state_dict keys of
+# UniterForPretraining: uniter.*, cls.predictions.*, feat_regress.*, region_classifier.*, itm_output.*)
+# ----------------------------------------------------------------------------------------------
+def _masked_hidden(hidden, mask):
+    """model/pretrain.py:129-133."""
+    mask = mask.unsqueeze(-1).expand_as(hidden)
+    return hidden[mask].contiguous().view(-1, hidden.size(-1))
+
+
+def _transform(sd, pre_dense, pre_ln, x):
+    """dense -> gelu -> LayerNorm (layer.py:196-200; pretrain.py:23-25, 40-42)."""
+    h = gelu(F.linear(x, sd[pre_dense + "weight"], sd[pre_dense + "bias"]))
+    return layer_norm(h, sd[pre_ln + "weight"], sd[pre_ln + "bias"])
+
+
+def pretrain_forward(sd, cfg, batch, task, compute_loss=True):
+    """UniterForPretraining.forward (model/pretrain.py:65-233), eval mode."""
+    kw = dict(input_ids=batch["input_ids"], position_ids=batch["position_ids"], img_feat=batch["img_feat"],
+              img_pos_feat=batch["img_pos_feat"], attention_mask=batch["attn_masks"],
+              gather_index=batch["gather_index"], output_all_encoded_layers=False, pre="uniter.")
+    if task == "mlm":
+        seq = uniter_forward(sd, cfg, **kw)[:, :batch["input_ids"].size(1), :]
+        lab = batch["txt_labels"]
+        h = _transform(sd, "cls.predictions.transform.dense.", "cls.predictions.transform.LayerNorm.",
+                       _masked_hidden(seq, lab != -1))
+        scores = F.linear(h, sd["cls.predictions.decoder.weight"]) + sd["cls.predictions.bias"]
+        return F.cross_entropy(scores, lab[lab != -1], reduction="none") if compute_loss else scores
+    if task == "mrfr":
+        seq = uniter_forward(sd, cfg, img_masks=batch["img_masks"], **kw)
+        h = _transform(sd, "feat_regress.net.0.", "feat_regress.net.2.", _masked_hidden(seq, batch["img_mask_tgt"]))
+        pred = F.linear(h, sd["feat_regress.weight"].t(), sd["feat_regress.bias"])
+        return F.mse_loss(pred, batch["feat_targets"], reduction="none") if compute_loss else pred
+    if task == "itm":
+        seq = uniter_forward(sd, cfg, **kw)
+        scores = F.linear(pooler(sd, "uniter.pooler.", seq), sd["itm_output.weight"], sd["itm_output.bias"])
+        ot = None
+        if batch.get("ot_inputs") is not None:
+            oi = batch["ot_inputs"]
+            b, tl, il = seq.size(0), batch["input_ids"].size(1), batch["img_feat"].size(1)
+            max_l = max(oi["scatter_max"] + 1, tl + il)
+            idx = oi["ot_scatter"].unsqueeze(-1).expand_as(seq)
+            ctx = torch.zeros(b, max_l, seq.size(-1), dtype=seq.dtype).scatter_(dim=1, index=idx, src=seq)
+            ot, _, _ = optimal_transport_dist(ctx[:, :tl].float(), ctx[:, tl:tl + il].float(), oi["txt_pad"], oi["img_pad"])
+        loss = F.cross_entropy(scores, batch["targets"], reduction="none") if compute_loss else scores
+        return loss, ot
+    if task.startswith("mrc"):
+        seq = uniter_forward(sd, cfg, img_masks=batch["img_masks"], **kw)
+        h = _transform(sd, "region_classifier.net.0.", "region_classifier.net.2.",
+                       _masked_hidden(seq, batch["img_mask_tgt"]))
+        pred = F.linear(h, sd["region_classifier.net.3.weight"], sd["region_classifier.net.3.bias"])
+        if not compute_loss:
+            return pred
+        if "kl" in task:
+            return F.kl_div(F.log_softmax(pred, dim=-1), batch["label_targets"], reduction="none")
+        tgt = torch.max(batch["label_targets"][:, 1:], dim=-1)[1] + 1
+        return F.cross_entropy(pred, tgt, ignore_index=0, reduction="none")
+    raise ValueError("invalid task")
+
+
+def synth_pretrain_batch(B, T, R, seed=77, img_dim=2048, vocab=28996, label_dim=1601, min_txt=8, min_bb=36):
+    """Synthetic multi-task batch with the keys of data/pretrain_{mlm,mrfr,itm}.py collates and an
+    ot_inputs dict whose semantics follow model/pretrain.py:169-190."""
+    b = synth_batch(B, T, R, seed=seed, variable=True, img_dim=img_dim, vocab=vocab, min_txt=min_txt, min_bb=min_bb)
+    g = torch.Generator().manual_seed(seed + 1)
+    tl, nb = b["txt_lens"], b["num_bbs"]
+    L = b["attn_mask"].shape[1]
+    maxR = b["img_feat"].shape[1]
+    txt_labels = torch.full((B, T), -1, dtype=torch.long)
+    img_masks = torch.zeros(B, maxR, dtype=torch.bool)
+    img_mask_tgt = torch.zeros(B, L, dtype=torch.bool)
+    ot_scatter = torch.full((B, L), T + maxR, dtype=torch.long)
+    for i in range(B):
+        m = torch.rand(tl[i], generator=g) < 0.15
+        m[int(torch.randint(0, tl[i], (1,), generator=g))] = True
+        txt_labels[i, :tl[i]][m] = b["input_ids"][i, :tl[i]][m]
+        r = torch.rand(nb[i], generator=g) < 0.15
+        r[int(torch.randint(0, nb[i], (1,), generator=g))] = True
+        img_masks[i, :nb[i]] = r
+        img_mask_tgt[i, tl[i]:tl[i] + nb[i]] = r
+        ot_scatter[i, :tl[i]] = torch.arange(tl[i])
+        ot_scatter[i, tl[i]:tl[i] + nb[i]] = T + torch.arange(nb[i])
+    feat_targets = b["img_feat"][img_masks].clone()
+    label_targets = torch.softmax(torch.randn(int(img_masks.sum()), label_dim, generator=g), -1)
+    out = dict(b)
+    out.update(attn_masks=b["attn_mask"], txt_labels=txt_labels, img_masks=img_masks, img_mask_tgt=img_mask_tgt,
+               feat_targets=feat_targets, label_targets=label_targets,
+               targets=(torch.rand(B, generator=g) < 0.5).long(),
+               ot_inputs=dict(ot_scatter=ot_scatter, scatter_max=T + maxR,
+                              txt_pad=torch.arange(T).unsqueeze(0) >= torch.tensor(tl).unsqueeze(1),
+                              img_pad=torch.arange(maxR).unsqueeze(0) >= torch.tensor(nb).unsqueeze(1)))
+    return out

@@ -386,3 +386,122 @@ def test_grad_accumulation_and_zero_grad_set_to_none():
     with torch.no_grad():
         l_after = m(**_kw(b))
     assert torch.isfinite(l_after).all()
+
+
+# ----------------------------------------------------------------------------------------------
+# optimal transport (model/ot.py): golden vectors from the unmodified reference + oracle
+# ----------------------------------------------------------------------------------------------
+def test_ot_against_reference_golden(golden_dir):
+    """IPOT plan rel error <= 1e-3, OT distance rel <= 1e-3 (BASELINE.json north_star)."""
+    _require_gpu()
+    from meme_challenge_b200.model import ot
+    g = np.load(os.path.join(golden_dir, "ot.npz"))
+    txt, img = torch.from_numpy(g["txt"]).to(DEV), torch.from_numpy(g["img"]).to(DEV)
+    txt_pad, img_pad = torch.from_numpy(g["txt_pad"]).to(DEV), torch.from_numpy(g["img_pad"]).to(DEV)
+    cost = ot.cost_matrix_cosine(txt, img)
+    assert (cost.cpu() - torch.from_numpy(g["cost"])).abs().max() < 1e-5
+    dist, T, _ = ot.optimal_transport_plan(txt, img, txt_pad, img_pad)
+    Tref = torch.from_numpy(g["T"])
+    assert (T.cpu() - Tref).norm() / Tref.norm() <= 1e-3
+    dref = torch.from_numpy(g["dist"])
+    assert ((dist.cpu() - dref).abs() / dref.abs()).max() <= 1e-3
+    # the reference-signature ipot() entry point
+    joint = txt_pad.unsqueeze(-1) | img_pad.unsqueeze(-2)
+    cm = cost.masked_fill(joint, 0)
+    T2 = ot.ipot(cm, (6 - txt_pad.sum(1)).float(), txt_pad, (9 - img_pad.sum(1)).float(), img_pad, joint, 0.5, 50, 1)
+    assert (T2.cpu() - Tref).norm() / Tref.norm() <= 1e-3
+
+
+def test_ot_c5_shape_and_gradient_against_oracle():
+    """C5 shape: M = 64 tokens, N = 100 regions, D = 768, ragged pads; distance + d/d(emb)."""
+    _require_gpu()
+    from meme_challenge_b200.model import ot
+    torch.manual_seed(8)
+    B, M, N, D = 16, 64, 100, 768
+    txt = torch.randn(B, M, D)
+    img = torch.randn(B, N, D)
+    tl = torch.randint(8, M + 1, (B,))
+    nb = torch.randint(36, N + 1, (B,))
+    txt_pad = torch.arange(M).unsqueeze(0) >= tl.unsqueeze(1)
+    img_pad = torch.arange(N).unsqueeze(0) >= nb.unsqueeze(1)
+    xr, yr = txt.clone().requires_grad_(True), img.clone().requires_grad_(True)
+    dref, Tref, _ = O.optimal_transport_dist(xr, yr, txt_pad, img_pad)
+    w = torch.randn(B)
+    (dref * w).sum().backward()
+    x, y = txt.to(DEV).requires_grad_(True), img.to(DEV).requires_grad_(True)
+    dist, T, _ = ot.optimal_transport_plan(x, y, txt_pad.to(DEV), img_pad.to(DEV))
+    (dist * w.to(DEV)).sum().backward()
+    assert (T.cpu() - Tref).norm() / Tref.norm() <= 1e-3
+    assert ((dist.detach().cpu() - dref.detach()).abs() / dref.detach().abs()).max() <= 1e-3
+    assert (x.grad.cpu() - xr.grad).norm() / xr.grad.norm() <= 1e-3
+    assert (y.grad.cpu() - yr.grad).norm() / yr.grad.norm() <= 1e-3
+    # marginals of the plan: rows/cols sum to 1/len on the valid block
+    s = T.sum((1, 2)).cpu()
+    assert torch.allclose(s, torch.ones(B), atol=1e-3)
+
+
+# ----------------------------------------------------------------------------------------------
+# pretraining heads (model/pretrain.py) against golden losses from the unmodified reference
+# ----------------------------------------------------------------------------------------------
+def _pretrain_setup(golden_dir):
+    from meme_challenge_b200.model.model import UniterConfig
+    from meme_challenge_b200.model.pretrain import UniterForPretraining
+    from oracle.make_golden import LABEL_DIM
+    g = np.load(os.path.join(golden_dir, "tiny_pretrain.npz"))
+    sd = {k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd.")}
+    b = {k[3:]: torch.from_numpy(g[k]).to(DEV) for k in g.files if k.startswith("in.")}
+    b["ot_inputs"] = {k[3:]: (torch.from_numpy(g[k]).to(DEV) if g[k].ndim else int(g[k])) for k in g.files if k.startswith("ot.")}
+    m = UniterForPretraining(UniterConfig.from_dict(TINY), IMG_DIM, LABEL_DIM)
+    assert list(m.state_dict().keys()) == list(sd.keys())
+    m.load_state_dict(sd, strict=True)
+    return g, sd, b, m.to(DEV).eval()
+
+
+def test_pretraining_tasks_against_reference_golden(golden_dir):
+    _require_gpu()
+    g, sd, b, m = _pretrain_setup(golden_dir)
+    with torch.no_grad():
+        for task, rtol in (("mlm", 2e-2), ("mrfr", 5e-2), ("itm", 2e-2), ("mrc-kl", 5e-2), ("mrc", 2e-2)):
+            got = m(b, task).float().cpu().numpy()
+            want = g["loss." + task]
+            assert got.shape == want.shape, task
+            err = np.abs(got - want).max() / (np.abs(want).max() + 1e-6)
+            assert err < rtol, (task, err)
+        scores = m(b, "mlm", compute_loss=False).float().cpu().numpy()
+        assert np.abs(scores - g["scores.mlm"]).max() < 2e-2
+    # ITM computes the OT distance like the reference does (and drops it); check it against the oracle
+    bc = {k: (v.cpu() if torch.is_tensor(v) else v) for k, v in b.items() if k != "ot_inputs"}
+    bc["ot_inputs"] = {k: (v.cpu() if torch.is_tensor(v) else v) for k, v in b["ot_inputs"].items()}
+    with torch.no_grad():
+        _, ot_ref = O.pretrain_forward(sd, TINY, bc, "itm")
+    pos, neg = m.last_ot_loss
+    tgt = b["targets"].cpu()
+    assert torch.allclose(pos.float().cpu(), ot_ref[tgt == 1], rtol=3e-2, atol=1e-3)
+    assert torch.allclose(neg.float().cpu(), ot_ref[tgt == 0], rtol=3e-2, atol=1e-3)
+    with pytest.raises(ValueError):
+        m(b, "nope")
+
+
+def test_pretraining_gradients_against_oracle(golden_dir):
+    """MLM + MRFR backward through the tied decoder / feat_regress weights."""
+    _require_gpu()
+    g, sd, b, m = _pretrain_setup(golden_dir)
+    bc = {k: (v.cpu() if torch.is_tensor(v) else v) for k, v in b.items() if k != "ot_inputs"}
+    for task in ("mlm", "mrfr"):
+        for p in m.parameters():
+            p.grad = None
+        m(b, task).float().mean().backward()
+        sdr = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+        sdr["cls.predictions.decoder.weight"] = sdr["uniter.embeddings.word_embeddings.weight"]
+        sdr["feat_regress.weight"] = sdr["uniter.img_embeddings.img_linear.weight"]
+        O.pretrain_forward(sdr, TINY, bc, task).mean().backward()
+        checked = 0
+        for n, p in m.named_parameters():
+            want = sdr[n].grad
+            if want is None or want.abs().max() < 1e-7:
+                continue
+            assert p.grad is not None, (task, n)
+            c = _cos(p.grad.detach().cpu(), want)
+            assert c > 0.98, (task, n, c)
+            checked += 1
+        assert checked > 30

@@ -106,3 +106,27 @@ def test_adam_l2_step_matches_torch():
         cur, _ = O.adam_l2_step(cur, gs, state, names, 3e-3, 1e-3, 2, 5)
     for a, b in zip(cur, tp):
         np.testing.assert_allclose(a.numpy(), b.detach().numpy(), rtol=1e-5, atol=1e-7)
+
+
+def _pretrain_golden(golden_dir):
+    g = _load(golden_dir, "tiny_pretrain.npz")
+    sd = {k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd.")}
+    b = {k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("in.")}
+    oi = {k[3:]: (torch.from_numpy(g[k]) if g[k].ndim else int(g[k])) for k in g.files if k.startswith("ot.")}
+    b["ot_inputs"] = oi
+    return g, sd, b
+
+
+def test_pretraining_heads_match_reference(golden_dir):
+    """oracle pretrain_forward vs the unmodified UniterForPretraining (model/pretrain.py:65-233)."""
+    from oracle.make_golden import TINY
+    g, sd, b = _pretrain_golden(golden_dir)
+    with torch.no_grad():
+        np.testing.assert_allclose(O.pretrain_forward(sd, TINY, b, "mlm").numpy(), g["loss.mlm"], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(O.pretrain_forward(sd, TINY, b, "mlm", False).numpy(), g["scores.mlm"], rtol=0, atol=2e-6)
+        np.testing.assert_allclose(O.pretrain_forward(sd, TINY, b, "mrfr").numpy(), g["loss.mrfr"], rtol=1e-4, atol=1e-6)
+        itm, ot = O.pretrain_forward(sd, TINY, b, "itm")
+        np.testing.assert_allclose(itm.numpy(), g["loss.itm"], rtol=1e-5, atol=1e-6)
+        assert ot.shape == (4,) and torch.isfinite(ot).all()
+        np.testing.assert_allclose(O.pretrain_forward(sd, TINY, b, "mrc-kl").numpy(), g["loss.mrc-kl"], rtol=1e-4, atol=1e-7)
+        np.testing.assert_allclose(O.pretrain_forward(sd, TINY, b, "mrc").numpy(), g["loss.mrc"], rtol=1e-5, atol=1e-6)
