@@ -108,6 +108,61 @@ def _cpu_fwd_bwd_memes_per_s(batch_memes, iters, warmup, threads):
     return batch_memes * len(times) / sum(times), sum(times)
 
 
+def _gemm_roofline(dev):
+    """Per optimizer step: (sum of GEMM durations in ms, sum of algorithmic FLOPs, launches, detail)."""
+    from meme_challenge_b200 import _lib, ops
+    M, H, I, D, NR = B * (T + R), BASE["hidden_size"], BASE["intermediate_size"], 2048, B * R
+    E = _lib
+    per_layer = [("qkv_fwd", M, 3 * H, H, 0, 0, E.EPI_STORE), ("attn_out_fwd", M, H, H, 0, 0, E.EPI_BIAS_DROP_RES),
+                 ("ffn1_fwd", M, I, H, 0, 0, E.EPI_BIAS_GELU), ("ffn2_fwd", M, H, I, 0, 0, E.EPI_BIAS_DROP_RES),
+                 ("ffn2_wgrad", H, I, M, 1, 1, E.EPI_ATOMIC_F32), ("ffn2_dgrad", M, I, H, 0, 1, E.EPI_DGELU),
+                 ("ffn1_wgrad", I, H, M, 1, 1, E.EPI_ATOMIC_F32), ("ffn1_dgrad", M, H, I, 0, 1, E.EPI_ADD),
+                 ("attn_out_wgrad", H, H, M, 1, 1, E.EPI_ATOMIC_F32), ("attn_out_dgrad", M, H, H, 0, 1, E.EPI_STORE),
+                 ("qkv_wgrad", 3 * H, H, M, 1, 1, E.EPI_ATOMIC_F32), ("qkv_dgrad", M, H, 3 * H, 0, 1, E.EPI_ADD)]
+    shapes = [(n, 2 * BASE["num_hidden_layers"], m, nn, k, am, bm, ep) for (n, m, nn, k, am, bm, ep) in per_layer]
+    shapes += [("img_linear_fwd", 2, NR, H, D, 0, 0, E.EPI_STORE_F32), ("img_linear_wgrad", 2, H, D, NR, 1, 1, E.EPI_ATOMIC_F32)]
+    tot_ms = tot_fl = 0.0
+    launches = 0
+    detail = {}
+    reps = 20
+    for (name, count, m, n, k, am, bm, ep) in shapes:
+        sets = []
+        for _ in range(2):
+            a = torch.randn((k, m) if am else (m, k), device=dev).bfloat16()
+            b = torch.randn((k, n) if bm else (n, k), device=dev).bfloat16()
+            f32 = ep in (E.EPI_ATOMIC_F32, E.EPI_STORE_F32)
+            kw = dict(a_mn=bool(am), b_mn=bool(bm), epilogue=ep,
+                      out=torch.zeros(m, n, device=dev, dtype=torch.float32 if f32 else torch.bfloat16))
+            if ep in (E.EPI_STORE, E.EPI_BIAS_DROP_RES, E.EPI_BIAS_GELU, E.EPI_STORE_F32):
+                kw["bias"] = torch.randn(n, device=dev)
+            if ep in (E.EPI_BIAS_DROP_RES, E.EPI_ADD, E.EPI_DGELU):
+                kw["res"] = torch.randn(m, n, device=dev).bfloat16()
+            if ep == E.EPI_BIAS_GELU:
+                kw["out2"] = torch.empty(m, n, device=dev, dtype=torch.bfloat16)
+            sets.append((a, b, kw))
+        for a, b, kw in sets:
+            ops.gemm(a, b, **kw)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for i in range(reps):
+                a, b, kw = sets[i % 2]
+                ops.gemm(a, b, **kw)
+        g.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        us = 1e3 * e0.elapsed_time(e1) / reps
+        detail[name] = round(us, 2)
+        tot_ms += count * us * 1e-3
+        tot_fl += count * 2.0 * m * n * k
+        launches += count
+    return tot_ms, tot_fl, launches, detail
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -138,7 +193,8 @@ def run_b200(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     L = _lib.lib()
 
     torch.manual_seed(0)
@@ -230,26 +286,19 @@ def run_b200(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, ms_e2e = t.tolist()
 
-    # ---- roofline leg: every tcgen05 GEMM launch of eager steps timed with CUDA events
+    # ---- roofline leg (rank 0, no collectives): every GEMM shape of the step, timed live with CUDA
+    # events around a captured graph of back-to-back launches (host launch gaps excluded)
     roof = None
     if rank == 0:
         sus, burst, hbm, how = _peaks()
-        prof_steps = 2
-        ts.step(devb[:ACCUM])
-        torch.cuda.synchronize()
-        L.b200u_prof_enable(prof_steps * 400)
-        for i in range(prof_steps):
-            ts.step(devb[:ACCUM])
-        import ctypes
-        tms, tfl, cnt = ctypes.c_double(), ctypes.c_double(), ctypes.c_int()
-        L.b200u_prof_collect(ctypes.byref(tms), ctypes.byref(tfl), ctypes.byref(cnt))
-        ach = tfl.value / (tms.value * 1e-3) / 1e12 if tms.value > 0 else 0.0
+        tms, tfl, nlaunch, detail = _gemm_roofline(dev)
+        ach = tfl / (tms * 1e-3) / 1e12
         roof = {"bound": "tensor", "achieved": round(ach, 1), "peak": sus, "unit": "TFLOP/s",
                 "frac": round(ach / sus, 4), "traffic": None,
-                "kernel": "gemm_tc_kernel (tcgen05+TMA bf16 GEMM family: %d launches/step, avg %.2f us, "
-                          "2MNK FLOPs each; peak = sustained cuBLAS bf16 of %s)" % (
-                              cnt.value // prof_steps, 1e3 * tms.value / max(1, cnt.value), how),
-                "gemm_ms_per_step": round(tms.value / prof_steps, 3)}
+                "kernel": "gemm_tc_kernel (tcgen05+TMA bf16 GEMM family): %d launches per optimizer step, each shape "
+                          "timed as 20 back-to-back launches in a CUDA graph; achieved = sum(2MNK) / sum(duration); "
+                          "peak = sustained cuBLAS bf16 (%s)" % (nlaunch, how),
+                "gemm_ms_per_step": round(tms, 3), "per_shape_us": detail}
 
     if rank == 0:
         memes = args.steps * ACCUM * B * world
@@ -287,7 +336,7 @@ def run_b200(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-graph", action="store_true")

@@ -33,6 +33,48 @@ def cosine_with_warmup(step, warmup_steps, total_steps):
     return max(0.0, 0.5 * (1.0 + math.cos(math.pi * progress)))
 
 
+class GradBuckets(object):
+    """Per-layer gradient buckets over ONE flat gradient buffer (no packing copies).
+
+    `entries` is the flat layout [(parameter name, offset)] in module order. Bucket 0 covers the
+    embeddings (everything before encoder layer 0), bucket i+1 covers encoder layer i, and the last
+    bucket also takes whatever follows the last layer (pooler, classification head). Buckets are
+    reduced with async all_reduce(SUM) as soon as the owning layer's backward is enqueued, i.e. in
+    reverse layer order, and `wait()` joins them before the optimizer; the 1/world averaging is
+    folded into the optimizer's gradient scale. Works on any backend (NCCL on GPUs, gloo in the
+    CPU tests)."""
+
+    def __init__(self, entries, flat_grad, process_group=None, world=1):
+        self.grad = flat_grad
+        self.pg = process_group
+        self.world = world
+        n = flat_grad.numel()
+        first = {}
+        for name, off in entries:
+            if "encoder.layer." in name:
+                l = int(name.split("encoder.layer.")[1].split(".")[0])
+                first.setdefault(l, off)
+        cuts = [first[l] for l in sorted(first)]
+        bounds = [0] + cuts + [n]
+        self.segments = [(bounds[i], bounds[i + 1]) for i in range(len(bounds) - 1)]
+        self.pending = []
+        self.reduced = []
+
+    def reduce_bucket(self, idx):
+        lo, hi = self.segments[idx]
+        self.reduced.append(idx)
+        if hi <= lo or self.world <= 1:
+            return
+        self.pending.append(torch.distributed.all_reduce(self.grad[lo:hi], group=self.pg, async_op=True))
+
+    def wait(self):
+        for w in self.pending:
+            w.wait()
+        self.pending = []
+        order, self.reduced = self.reduced, []
+        return order
+
+
 class TrainStep(object):
     def __init__(self, model, lr=3e-5, weight_decay=1e-3, betas=(0.9, 0.999), eps=1e-8,
                  gradient_accumulation=2, max_grad_norm=5.0, pos_wt=1.8, process_group=None,
@@ -83,41 +125,22 @@ class TrainStep(object):
         self.chunk_run = cr.to(torch.int32).to(dev)
         self.num_runs = len(wds)
 
-        # gradient buckets in backward order: [head + pooler + last layer], ..., layer 0, embeddings
-        self.buckets = self._make_buckets()
-        self._pending = []
+        # gradient buckets: index 0 = embeddings, 1.. = encoder layers (the last also holds pooler + head)
+        self.comm = GradBuckets([(e[0], e[2]) for e in store.entries], store.grad, process_group, self.world)
+        self.buckets = self.comm.segments
         self._graph = None
         self._static = None
         self.um._layer_grad_ready_cb = None
         store.refresh_shadow(force=True)
 
     # ------------------------------------------------------------------ buckets / comm
-    def _make_buckets(self):
-        ent = self.store.entries
-        first_layer = {}
-        for i, (name, p, off, cnt) in enumerate(ent):
-            if ".encoder.layer." in name or name.startswith("encoder.layer."):
-                l = int(name.split("encoder.layer.")[1].split(".")[0])
-                first_layer.setdefault(l, off)
-        n = self.store.flat.numel()
-        layers = sorted(first_layer)
-        cuts = [first_layer[l] for l in layers]          # start offset of each layer
-        bounds = [0] + cuts + [n]
-        # segments: [0, layer0) = embeddings ; [layer_i, layer_{i+1}) ; [last layer, n) incl. pooler/head
-        segs = [(bounds[i], bounds[i + 1]) for i in range(len(bounds) - 1)]
-        return segs  # index 0 = embeddings, 1.. = layers (last one also holds pooler + head)
-
-    def _allreduce_bucket(self, seg):
-        lo, hi = seg
-        if hi <= lo:
-            return
-        w = torch.distributed.all_reduce(self.store.grad[lo:hi], group=self.pg, async_op=True)
-        self._pending.append(w)
+    def _allreduce_bucket(self, idx):
+        self.comm.reduce_bucket(idx)
 
     def _on_layer_done(self, layer_idx):
         # called (from the autograd thread) once the backward of encoder layer `layer_idx` has been
         # enqueued: its bucket is final for this optimizer step, start the all-reduce now
-        self._allreduce_bucket(self.buckets[layer_idx + 1])
+        self.comm.reduce_bucket(layer_idx + 1)
 
     # ------------------------------------------------------------------ one micro-batch
     def micro_step(self, batch, last):
@@ -133,16 +156,14 @@ class TrainStep(object):
         self.um._layer_grad_ready_cb = None
         if comm:
             if not self.overlap_comm:
-                for seg in reversed(self.buckets[1:]):
-                    self._allreduce_bucket(seg)
-            self._allreduce_bucket(self.buckets[0])
+                for i in range(len(self.buckets) - 1, 0, -1):
+                    self._allreduce_bucket(i)
+            self._allreduce_bucket(0)
         return loss, probs
 
     # ------------------------------------------------------------------ optimizer
     def optimizer_step(self):
-        for w in self._pending:
-            w.wait()
-        self._pending = []
+        self.comm.wait()
         g = self.store.grad
         n = g.numel()
         self.sumsq.zero_()
