@@ -200,7 +200,8 @@ def run_b200(args, rank, world, local_rank):
     torch.manual_seed(0)
     cfg = UniterConfig.from_dict(BASE)
     model = MemeUniter(UniterModel(cfg, 2048), 768, 1).to(dev).train()
-    ts = TrainStep(model, lr=3e-5, weight_decay=1e-3, gradient_accumulation=ACCUM, max_grad_norm=5.0, pos_wt=1.8)
+    ts = TrainStep(model, lr=3e-5, weight_decay=1e-3, gradient_accumulation=ACCUM, max_grad_norm=5.0, pos_wt=1.8,
+                   overlap_comm=not args.graph_dp)
 
     # synthetic data: a ring of distinct host batches (pinned) and their device copies
     n_sets = 4
@@ -220,7 +221,9 @@ def run_b200(args, rank, world, local_rank):
         torch.cuda.synchronize()
 
     # ---- capture the whole optimizer step in a CUDA graph (falls back to eager on failure)
-    use_graph = not args.no_graph
+    # N > 1: the overlapped NCCL bucket all-reduces are issued from autograd hooks, which cannot be
+    # stream-captured; data-parallel runs therefore execute the same TrainStep eagerly.
+    use_graph = (not args.no_graph) and (world == 1 or args.graph_dp)
     launches_per_step = None
     if use_graph:
         try:
@@ -341,6 +344,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--graph-dp", action="store_true", help="experimental: CUDA-graph the DP step (no comm overlap)")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup)
     rank = int(os.environ.get("RANK", "0"))

@@ -95,23 +95,32 @@ __device__ __forceinline__ uint64_t load_seed(const DropoutCfg& d) {
 // erf via Abramowitz-Stegun 7.1.26 (|abs error| <= 1.5e-7, i.e. fp32-level for GELU): one
 // reciprocal, one exp2 and five FMAs instead of erff()'s ~40-instruction polynomial, so the fused
 // GEMM epilogues stay cheaper than the main loop they overlap with.
+__device__ __forceinline__ float rcp_approx(float x) {  // MUFU.RCP, callers guarantee x >= 1
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float ex2_approx(float x) {  // MUFU.EX2
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 __device__ __forceinline__ float erf_fast(float x) {
     const float ax = fabsf(x);
-    const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+    const float t = rcp_approx(fmaf(0.3275911f, ax, 1.0f));
     float p = fmaf(1.061405429f, t, -1.453152027f);
     p = fmaf(p, t, 1.421413741f);
     p = fmaf(p, t, -0.284496736f);
     p = fmaf(p, t, 0.254829592f);
-    const float e = exp2f(-1.4426950408889634f * ax * ax);
-    const float r = fmaf(-p * t, e, 1.0f);
-    return copysignf(r, x);
+    const float e = ex2_approx(-1.4426950408889634f * ax * ax);
+    return copysignf(fmaf(-p * t, e, 1.0f), x);
 }
 __device__ __forceinline__ float gelu_erf(float x) {
     return x * 0.5f * (1.0f + erf_fast(x * 0.70710678118654752440f));
 }
 __device__ __forceinline__ float gelu_erf_grad(float x) {
     float cdf = 0.5f * (1.0f + erf_fast(x * 0.70710678118654752440f));
-    float pdf = 0.39894228040143267794f * exp2f(-0.72134752044448170368f * x * x);
+    float pdf = 0.39894228040143267794f * ex2_approx(-0.72134752044448170368f * x * x);
     return cdf + x * pdf;
 }
 

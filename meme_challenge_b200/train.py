@@ -59,13 +59,17 @@ class GradBuckets(object):
         self.segments = [(bounds[i], bounds[i + 1]) for i in range(len(bounds) - 1)]
         self.pending = []
         self.reduced = []
+        self.sync = False  # True: blocking collectives on the current stream (graph-capturable)
 
     def reduce_bucket(self, idx):
         lo, hi = self.segments[idx]
         self.reduced.append(idx)
         if hi <= lo or self.world <= 1:
             return
-        self.pending.append(torch.distributed.all_reduce(self.grad[lo:hi], group=self.pg, async_op=True))
+        if self.sync:
+            torch.distributed.all_reduce(self.grad[lo:hi], group=self.pg)
+        else:
+            self.pending.append(torch.distributed.all_reduce(self.grad[lo:hi], group=self.pg, async_op=True))
 
     def wait(self):
         for w in self.pending:
@@ -128,6 +132,7 @@ class TrainStep(object):
         # gradient buckets: index 0 = embeddings, 1.. = encoder layers (the last also holds pooler + head)
         self.comm = GradBuckets([(e[0], e[2]) for e in store.entries], store.grad, process_group, self.world)
         self.buckets = self.comm.segments
+        self.comm.sync = not overlap_comm
         self._graph = None
         self._static = None
         self.um._layer_grad_ready_cb = None
