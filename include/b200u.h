@@ -159,9 +159,12 @@ int b200u_pos_linear_wgrad(const void* dp, const float* pos7, float* dW, int n, 
  * lse f32 [B,heads,L] is saved for the backward, which writes dqkv [B*L, 3H]. */
 int b200u_attention_fwd(const void* qkv, const float* mask, void* ctx, float* lse, int B, int L,
                         int num_heads, int H, const b200u_dropout_t* drop, b200u_stream_t stream);
+/* scratch: caller-owned device buffer of b200u_attention_bwd_scratch_bytes(B, L, heads) bytes
+ * (bf16 probabilities and score gradients handed from the dQ launch to the dK/dV launch). */
+size_t b200u_attention_bwd_scratch_bytes(int B, int L, int num_heads);
 int b200u_attention_bwd(const void* qkv, const float* mask, const void* ctx, const void* dctx,
-                        const float* lse, void* dqkv, int B, int L, int num_heads, int H,
-                        const b200u_dropout_t* drop, b200u_stream_t stream);
+                        const float* lse, void* dqkv, void* scratch, int B, int L, int num_heads,
+                        int H, const b200u_dropout_t* drop, b200u_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * BertLayer.forward / its backward as one call each (model/layer.py:159-170). Weight matrices
@@ -206,6 +209,7 @@ typedef struct {
     void* dctx; /* bf16 [M,H]  */
     void* du;   /* bf16 [M,I]  */
     void* dqkv; /* bf16 [M,3H] */
+    void* attn; /* b200u_attention_bwd_scratch_bytes(B, L, heads) bytes */
 } b200u_layer_scratch_t;
 int b200u_bert_layer_fwd(const b200u_layer_params_t* p, const void* x0, const b200u_layer_saved_t* saved,
                          void* x2, b200u_stream_t stream);

@@ -34,7 +34,8 @@ SIGNATURES = {
     "b200u_embedding_scatter_add": (_i, [_p, _p, _i, _i, _ll, _p, _i, _i, _ll, _p]),
     "b200u_pos_linear_wgrad": (_i, [_p, _p, _p, _i, _i, _p]),
     "b200u_attention_fwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p, _p]),
-    "b200u_attention_bwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p]),
+    "b200u_attention_bwd_scratch_bytes": (_sz, [_i, _i, _i]),
+    "b200u_attention_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p]),
     "b200u_bert_layer_fwd": (_i, [_p, _p, _p, _p, _p]),
     "b200u_bert_layer_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p]),
     "b200u_pooler_fwd": (_i, [_p, _ll, _p, _p, _p, _i, _i, _p]),

@@ -221,222 +221,215 @@ attn_fwd_kernel(const bf16* __restrict__ qkv, const float* __restrict__ mask, bf
 }
 
 // ---------------------------------------------------------------------------------------
-// Backward. grid = (B*heads, ceil(L/64), 2). blockIdx.z == 0: dQ for a 64-row query tile (full
-// K, V in smem, keys swept in chunks of 32). blockIdx.z == 1: dK, dV for a 64-row key tile (full
-// Q, dO in smem, queries swept in chunks of 32). Probabilities are recomputed from the saved
-// log-sum-exp and the dropout mask is regenerated; no atomics, deterministic.
-//   D_i = sum_d dO[i,d] O[i,d] ; dPd = dO·Vᵀ ; dP = dropmask*scale*dPd ; dS = P*(dP - D_i)
-//   dQ = (dS/8)·K ; dK = (dS/8)ᵀ·Q ; dV = Pdᵀ·dO
+// Backward, two launches (the second consumes what the first leaves in L2):
+//  1. attn_bwd_dq_kernel, grid (B*heads, ceil(L/64)): a 64-row query tile against all keys in
+//     chunks of 32. Recomputes P from the saved log-sum-exp, regenerates the dropout mask, forms
+//         D_i = sum_d dO[i,d] O[i,d] ; dPd = dO·Vᵀ ; dP = dropmask*scale*dPd ; dS = P*(dP - D_i)/8
+//     accumulates dQ = dS·K and ALSO writes Pd = dropmask*scale*P and dS (bf16, [B*heads, L, LP])
+//     to a scratch buffer, so the element-wise work (exp2, RNG) is done once.
+//  2. attn_bwd_dkv_kernel, grid (B*heads, ceil(L/64)): a 64-row key tile; dV = Pdᵀ·dO and
+//     dK = dSᵀ·Q are plain tensor-core products over the scratch tiles (ldmatrix.trans A operands).
+// No atomics, deterministic.
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128, 3)
-attn_bwd_kernel(const bf16* __restrict__ qkv, const float* __restrict__ mask,
-                const bf16* __restrict__ ctx, const bf16* __restrict__ dctx,
-                const float* __restrict__ lse, bf16* __restrict__ dqkv, int L, int LP, int nh, int H,
-                DropoutCfg drop) {
+attn_bwd_dq_kernel(const bf16* __restrict__ qkv, const float* __restrict__ mask,
+                   const bf16* __restrict__ ctx, const bf16* __restrict__ dctx,
+                   const float* __restrict__ lse, bf16* __restrict__ dqkv, bf16* __restrict__ scrP,
+                   bf16* __restrict__ scrS, int L, int LP, int nh, int H, DropoutCfg drop) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
-    bf16* F0 = reinterpret_cast<bf16*>(smem_raw);  // full matrices: (K, V) for dQ ; (Q, dO) for dK/dV
-    bf16* F1 = F0 + LP * HD;
-    bf16* T0 = F1 + LP * HD;                       // 64-row tiles: (Q, dO) for dQ ; (K, V) for dK/dV
-    bf16* T1 = T0 + TQ * HD;
-    float* sM = reinterpret_cast<float*>(T1 + TQ * HD);
-    float* sLse = sM + LP;
-    float* sD = sLse + LP;
+    bf16* sK = reinterpret_cast<bf16*>(smem_raw);
+    bf16* sV = sK + LP * HD;
+    bf16* sQ = sV + LP * HD;
+    bf16* sdO = sQ + TQ * HD;
+    float* sM2 = reinterpret_cast<float*>(sdO + TQ * HD);  // additive mask * log2(e)
+    float* sL2 = sM2 + LP;                                 // lse * log2(e) of the tile rows
+    float* sD = sL2 + TQ;                                  // D of the tile rows
 
     const int bh = blockIdx.x, b = bh / nh, h = bh - b * nh;
     const int t0 = blockIdx.y * TQ;
-    const bool passA = blockIdx.z == 0;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ld = 3 * H;
     const bf16* base = qkv + (size_t)b * L * ld + h * HD;
     const bf16* dO = dctx + (size_t)b * L * H + h * HD;
     const bf16* O = ctx + (size_t)b * L * H + h * HD;
 
-    if (passA) {
-        load_tile(T0, base + (size_t)t0 * ld, ld, L - t0, TQ, tid, 128);   // Q tile
-        load_tile(T1, dO + (size_t)t0 * H, H, L - t0, TQ, tid, 128);       // dO tile
-        load_tile(F0, base + H, ld, L, LP, tid, 128);                      // K
-        load_tile(F1, base + 2 * H, ld, L, LP, tid, 128);                  // V
-    } else {
-        load_tile(T0, base + H + (size_t)t0 * ld, ld, L - t0, TQ, tid, 128);      // K tile
-        load_tile(T1, base + 2 * H + (size_t)t0 * ld, ld, L - t0, TQ, tid, 128);  // V tile
-        load_tile(F0, base, ld, L, LP, tid, 128);                                 // Q
-        load_tile(F1, dO, H, L, LP, tid, 128);                                    // dO
-    }
-    for (int j = tid; j < LP; j += 128) {
-        sM[j] = (j < L) ? mask[(size_t)b * L + j] : -INFINITY;
-        sLse[j] = (j < L) ? lse[(size_t)bh * L + j] : 0.f;
-    }
-    // D_i = rowsum(dO * O): 8 threads per row. dQ pass needs its tile rows, dK/dV pass all rows.
-    {
-        const int rows = passA ? TQ : LP;
-        const int roff = passA ? t0 : 0;
-        for (int i = tid >> 3; i < rows; i += 16) {
-            const int gi = roff + i;
-            float d = 0.f;
-            if (gi < L) {
-                const int ch = tid & 7;
-                uint4 ov = *reinterpret_cast<const uint4*>(O + (size_t)gi * H + ch * 8);
-                uint4 dv = *reinterpret_cast<const uint4*>(dO + (size_t)gi * H + ch * 8);
-                const uint32_t* op = &ov.x;
-                const uint32_t* dp = &dv.x;
+    load_tile(sQ, base + (size_t)t0 * ld, ld, L - t0, TQ, tid, 128);
+    load_tile(sdO, dO + (size_t)t0 * H, H, L - t0, TQ, tid, 128);
+    load_tile(sK, base + H, ld, L, LP, tid, 128);
+    load_tile(sV, base + 2 * H, ld, L, LP, tid, 128);
+    for (int j = tid; j < LP; j += 128) sM2[j] = (j < L) ? mask[(size_t)b * L + j] * LOG2E : -INFINITY;
+    for (int i = tid >> 3; i < TQ; i += 16) {  // D_i and lse_i of the tile rows: 8 threads per row
+        const int gi = t0 + i;
+        float d = 0.f;
+        if (gi < L) {
+            const int ch = tid & 7;
+            uint4 ov = *reinterpret_cast<const uint4*>(O + (size_t)gi * H + ch * 8);
+            uint4 dv = *reinterpret_cast<const uint4*>(dO + (size_t)gi * H + ch * 8);
+            const uint32_t* op = &ov.x;
+            const uint32_t* dp = &dv.x;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    float2 a = unpack_bf16(op[k]), c = unpack_bf16(dp[k]);
-                    d += a.x * c.x + a.y * c.y;
-                }
+            for (int k = 0; k < 4; ++k) {
+                float2 x = unpack_bf16(op[k]), y = unpack_bf16(dp[k]);
+                d += x.x * y.x + x.y * y.y;
             }
-            d += __shfl_xor_sync(0xffffffffu, d, 1);
-            d += __shfl_xor_sync(0xffffffffu, d, 2);
-            d += __shfl_xor_sync(0xffffffffu, d, 4);
-            if ((tid & 7) == 0 && gi < LP) sD[gi] = d;
+        }
+        d += __shfl_xor_sync(0xffffffffu, d, 1);
+        d += __shfl_xor_sync(0xffffffffu, d, 2);
+        d += __shfl_xor_sync(0xffffffffu, d, 4);
+        if ((tid & 7) == 0) {
+            sD[i] = d;
+            sL2[i] = (gi < L) ? lse[(size_t)bh * L + gi] * LOG2E : 0.f;
         }
     }
     __syncthreads();
 
-    const int r0 = t0 + warp * 16;  // first tile row of this warp (query for dQ, key for dK/dV)
+    const int r0 = t0 + warp * 16;
     if (r0 >= L) return;
     const uint32_t key = drop.thresh16 ? attn_key(load_seed(drop), drop.stream) : 0u;
     const int g = lane >> 2, t2 = (lane & 3) * 2;
     const int x0 = r0 + g, x1 = r0 + g + 8;
+    uint32_t qa[4][4], da[4][4];
+    load_a_frags(sQ, warp * 16, lane, qa);
+    load_a_frags(sdO, warp * 16, lane, da);
+    const float la = sL2[warp * 16 + g], lb = sL2[warp * 16 + g + 8];
+    const float Da = sD[warp * 16 + g], Db = sD[warp * 16 + g + 8];
+    const uint32_t pb0 = attn_pair_base(bh, x0, L), pb1 = attn_pair_base(bh, x1, L);
+    constexpr float SC = 0.125f * LOG2E;
+    bf16* pP0 = scrP + ((size_t)bh * L + x0) * LP;
+    bf16* pP1 = scrP + ((size_t)bh * L + x1) * LP;
+    bf16* pS0 = scrS + ((size_t)bh * L + x0) * LP;
+    bf16* pS1 = scrS + ((size_t)bh * L + x1) * LP;
+    float dq[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) dq[nt][0] = dq[nt][1] = dq[nt][2] = dq[nt][3] = 0.f;
+    for (int c0 = 0; c0 < LP; c0 += 32) {
+        float s[4][4], dp[4][4];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+            dp[nt][0] = dp[nt][1] = dp[nt][2] = dp[nt][3] = 0.f;
+        }
+#pragma unroll
+        for (int np = 0; np < 2; ++np) {
+            if (c0 + np * 16 < LP) {
+                mma_xt(s[2 * np], s[2 * np + 1], qa, sK, c0 + np * 16, lane);    // Q·Kᵀ
+                mma_xt(dp[2 * np], dp[2 * np + 1], da, sV, c0 + np * 16, lane);  // dO·Vᵀ
+            }
+        }
+#pragma unroll
+        for (int np = 0; np < 2; ++np) {
+            if (c0 + np * 16 < LP) {
+                uint32_t dsp[2][2], pdp[2][2];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int nt = 2 * np + e;
+                    const int j = c0 + nt * 8 + t2;
+                    const float ma = sM2[j], mb = sM2[j + 1];
+                    const float p0 = ex2_approx(fmaf(s[nt][0], SC, ma) - la);
+                    const float p1 = ex2_approx(fmaf(s[nt][1], SC, mb) - la);
+                    const float p2 = ex2_approx(fmaf(s[nt][2], SC, ma) - lb);
+                    const float p3 = ex2_approx(fmaf(s[nt][3], SC, mb) - lb);
+                    float k0 = 1.f, k1 = 1.f, k2 = 1.f, k3 = 1.f;
+                    if (drop.thresh16) {
+                        const uint32_t jp = (uint32_t)j >> 1;
+                        const uint32_t h0 = attn_rng(key, pb0 + jp), h1 = attn_rng(key, pb1 + jp);
+                        k0 = ((h0 & 0xffffu) >= drop.thresh16) ? drop.scale : 0.f;
+                        k1 = ((h0 >> 16) >= drop.thresh16) ? drop.scale : 0.f;
+                        k2 = ((h1 & 0xffffu) >= drop.thresh16) ? drop.scale : 0.f;
+                        k3 = ((h1 >> 16) >= drop.thresh16) ? drop.scale : 0.f;
+                    }
+                    dsp[e][0] = pack_bf16(p0 * (dp[nt][0] * k0 - Da) * 0.125f, p1 * (dp[nt][1] * k1 - Da) * 0.125f);
+                    dsp[e][1] = pack_bf16(p2 * (dp[nt][2] * k2 - Db) * 0.125f, p3 * (dp[nt][3] * k3 - Db) * 0.125f);
+                    pdp[e][0] = pack_bf16(p0 * k0, p1 * k1);
+                    pdp[e][1] = pack_bf16(p2 * k2, p3 * k3);
+                    if (x0 < L) {
+                        *reinterpret_cast<uint32_t*>(pP0 + j) = pdp[e][0];
+                        *reinterpret_cast<uint32_t*>(pS0 + j) = dsp[e][0];
+                    }
+                    if (x1 < L) {
+                        *reinterpret_cast<uint32_t*>(pP1 + j) = pdp[e][1];
+                        *reinterpret_cast<uint32_t*>(pS1 + j) = dsp[e][1];
+                    }
+                }
+                mma_x(dq, dsp[0][0], dsp[0][1], dsp[1][0], dsp[1][1], sK, c0 + np * 16, lane);
+            }
+        }
+    }
     bf16* dbase = dqkv + (size_t)b * L * ld + h * HD;
-    uint32_t ta[4][4], tb[4][4];
-    load_a_frags(T0, warp * 16, lane, ta);
-    load_a_frags(T1, warp * 16, lane, tb);
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+        if (x0 < L) *reinterpret_cast<uint32_t*>(dbase + (size_t)x0 * ld + nt * 8 + t2) = pack_bf16(dq[nt][0], dq[nt][1]);
+        if (x1 < L) *reinterpret_cast<uint32_t*>(dbase + (size_t)x1 * ld + nt * 8 + t2) = pack_bf16(dq[nt][2], dq[nt][3]);
+    }
+}
 
-    if (passA) {
-        // ---------------- dQ: rows = queries (x0, x1), columns = keys ----------------
-        const float la = sLse[x0 < LP ? x0 : LP - 1], lb = sLse[x1 < LP ? x1 : LP - 1];
-        const float Da = sD[x0 < LP ? x0 : LP - 1], Db = sD[x1 < LP ? x1 : LP - 1];
-        const uint32_t pb0 = attn_pair_base(bh, x0, L), pb1 = attn_pair_base(bh, x1, L);
-        float dq[8][4];
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt) dq[nt][0] = dq[nt][1] = dq[nt][2] = dq[nt][3] = 0.f;
-        for (int c0 = 0; c0 < L; c0 += 32) {
-            float s[4][4], dp[4][4];
-#pragma unroll
-            for (int nt = 0; nt < 4; ++nt) {
-                s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
-                dp[nt][0] = dp[nt][1] = dp[nt][2] = dp[nt][3] = 0.f;
-            }
-#pragma unroll
-            for (int np = 0; np < 2; ++np) {
-                if (c0 + np * 16 < L) {
-                    mma_xt(s[2 * np], s[2 * np + 1], ta, F0, c0 + np * 16, lane);    // Q·Kᵀ
-                    mma_xt(dp[2 * np], dp[2 * np + 1], tb, F1, c0 + np * 16, lane);  // dO·Vᵀ
-                }
-            }
-#pragma unroll
-            for (int np = 0; np < 2; ++np) {
-                if (c0 + np * 16 < L) {
-                    float ds[2][4];
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const int nt = 2 * np + e;
-                        const int j = c0 + nt * 8 + t2;
-                        const float ma = sM[j], mb = sM[j + 1];
-                        const float p0 = exp2f((s[nt][0] * 0.125f + ma - la) * LOG2E);
-                        const float p1 = exp2f((s[nt][1] * 0.125f + mb - la) * LOG2E);
-                        const float p2 = exp2f((s[nt][2] * 0.125f + ma - lb) * LOG2E);
-                        const float p3 = exp2f((s[nt][3] * 0.125f + mb - lb) * LOG2E);
-                        float d0 = dp[nt][0], d1 = dp[nt][1], d2 = dp[nt][2], d3 = dp[nt][3];
-                        if (drop.thresh16) {
-                            const uint32_t jp = (uint32_t)j >> 1;
-                            const uint32_t h0 = attn_rng(key, pb0 + jp), h1 = attn_rng(key, pb1 + jp);
-                            d0 = ((h0 & 0xffffu) >= drop.thresh16) ? d0 * drop.scale : 0.f;
-                            d1 = ((h0 >> 16) >= drop.thresh16) ? d1 * drop.scale : 0.f;
-                            d2 = ((h1 & 0xffffu) >= drop.thresh16) ? d2 * drop.scale : 0.f;
-                            d3 = ((h1 >> 16) >= drop.thresh16) ? d3 * drop.scale : 0.f;
-                        }
-                        ds[e][0] = p0 * (d0 - Da) * 0.125f; ds[e][1] = p1 * (d1 - Da) * 0.125f;
-                        ds[e][2] = p2 * (d2 - Db) * 0.125f; ds[e][3] = p3 * (d3 - Db) * 0.125f;
-                    }
-                    mma_x(dq, pack_bf16(ds[0][0], ds[0][1]), pack_bf16(ds[0][2], ds[0][3]),
-                          pack_bf16(ds[1][0], ds[1][1]), pack_bf16(ds[1][2], ds[1][3]), F0, c0 + np * 16, lane);
-                }
-            }
+// acc[8 n-tiles] += Xᵀ[m0..m0+15, k0..k0+15] · Y[k0..k0+15, 0..63]  with X, Y row-major swizzled
+// tiles whose ROWS are the reduction index (queries): A fragments come from ldmatrix.trans.
+__device__ __forceinline__ void mma_tn(float (&acc)[8][4], const bf16* X, const bf16* Y, int m0, int k0,
+                                       int lane) {
+    uint32_t a0, a1, a2, a3;
+    {
+        const int r = k0 + (lane & 7) + ((lane >> 4) & 1) * 8;
+        const int c = (m0 >> 3) + ((lane >> 3) & 1);
+        ldsm_x4_t(smem_u32(X + sw_off(r, c)), a0, a1, a2, a3);
+    }
+    mma_x(acc, a0, a1, a2, a3, Y, k0, lane);
+}
+
+__global__ void __launch_bounds__(128, 3)
+attn_bwd_dkv_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dctx,
+                    const bf16* __restrict__ scrP, const bf16* __restrict__ scrS,
+                    bf16* __restrict__ dqkv, int L, int LP, int nh, int H) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    bf16* sQ = reinterpret_cast<bf16*>(smem_raw);  // [LP][64]
+    bf16* sdO = sQ + LP * HD;                      // [LP][64]
+    bf16* sP = sdO + LP * HD;                      // [LP queries][64 keys of this tile]
+    bf16* sS = sP + LP * HD;
+
+    const int bh = blockIdx.x, b = bh / nh, h = bh - b * nh;
+    const int t0 = blockIdx.y * TQ;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ld = 3 * H;
+    const bf16* base = qkv + (size_t)b * L * ld + h * HD;
+    const bf16* dO = dctx + (size_t)b * L * H + h * HD;
+    load_tile(sQ, base, ld, L, LP, tid, 128);
+    load_tile(sdO, dO, H, L, LP, tid, 128);
+    // key columns t0..t0+63 of every query row; columns >= LP (last tile) are zero-filled
+    for (int i = tid; i < LP * 8; i += 128) {
+        const int r = i >> 3, ch = i & 7;
+        uint4 vp = make_uint4(0, 0, 0, 0), vs = make_uint4(0, 0, 0, 0);
+        if (r < L && t0 + ch * 8 < LP) {
+            vp = *reinterpret_cast<const uint4*>(scrP + ((size_t)bh * L + r) * LP + t0 + ch * 8);
+            vs = *reinterpret_cast<const uint4*>(scrS + ((size_t)bh * L + r) * LP + t0 + ch * 8);
         }
+        *reinterpret_cast<uint4*>(sP + sw_off(r, ch)) = vp;
+        *reinterpret_cast<uint4*>(sS + sw_off(r, ch)) = vs;
+    }
+    __syncthreads();
+    const int r0 = t0 + warp * 16;
+    if (r0 >= L) return;
+    float dk[8][4], dv[8][4];
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-            if (x0 < L) *reinterpret_cast<uint32_t*>(dbase + (size_t)x0 * ld + nt * 8 + t2) = pack_bf16(dq[nt][0], dq[nt][1]);
-            if (x1 < L) *reinterpret_cast<uint32_t*>(dbase + (size_t)x1 * ld + nt * 8 + t2) = pack_bf16(dq[nt][2], dq[nt][3]);
+    for (int nt = 0; nt < 8; ++nt) {
+        dk[nt][0] = dk[nt][1] = dk[nt][2] = dk[nt][3] = 0.f;
+        dv[nt][0] = dv[nt][1] = dv[nt][2] = dv[nt][3] = 0.f;
+    }
+    for (int k0 = 0; k0 < LP; k0 += 16) {
+        mma_tn(dv, sP, sdO, warp * 16, k0, lane);  // dV += Pdᵀ·dO
+        mma_tn(dk, sS, sQ, warp * 16, k0, lane);   // dK += dSᵀ·Q
+    }
+    const int g = lane >> 2, t2 = (lane & 3) * 2;
+    const int x0 = r0 + g, x1 = r0 + g + 8;
+    bf16* dbase = dqkv + (size_t)b * L * ld + h * HD;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+        if (x0 < L) {
+            *reinterpret_cast<uint32_t*>(dbase + (size_t)x0 * ld + H + nt * 8 + t2) = pack_bf16(dk[nt][0], dk[nt][1]);
+            *reinterpret_cast<uint32_t*>(dbase + (size_t)x0 * ld + 2 * H + nt * 8 + t2) = pack_bf16(dv[nt][0], dv[nt][1]);
         }
-    } else {
-        // ---------------- dK, dV: rows = keys (x0, x1), columns = queries ----------------
-        const int Lh = (L + 1) >> 1;
-        const float ma = sM[x0 < LP ? x0 : LP - 1], mb = sM[x1 < LP ? x1 : LP - 1];
-        float dk[8][4], dv[8][4];
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-            dk[nt][0] = dk[nt][1] = dk[nt][2] = dk[nt][3] = 0.f;
-            dv[nt][0] = dv[nt][1] = dv[nt][2] = dv[nt][3] = 0.f;
-        }
-        for (int c0 = 0; c0 < L; c0 += 32) {
-            float s[4][4], dp[4][4];
-#pragma unroll
-            for (int nt = 0; nt < 4; ++nt) {
-                s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
-                dp[nt][0] = dp[nt][1] = dp[nt][2] = dp[nt][3] = 0.f;
-            }
-#pragma unroll
-            for (int np = 0; np < 2; ++np) {
-                if (c0 + np * 16 < L) {
-                    mma_xt(s[2 * np], s[2 * np + 1], ta, F0, c0 + np * 16, lane);    // K·Qᵀ  = Sᵀ
-                    mma_xt(dp[2 * np], dp[2 * np + 1], tb, F1, c0 + np * 16, lane);  // V·dOᵀ = dPdᵀ
-                }
-            }
-#pragma unroll
-            for (int np = 0; np < 2; ++np) {
-                if (c0 + np * 16 < L) {
-                    float pd[2][4], ds[2][4];
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const int nt = 2 * np + e;
-                        const int i = c0 + nt * 8 + t2;  // query index of columns i, i+1
-                        const float li = sLse[i], lj = sLse[i + 1];
-                        const float Di = sD[i], Dj = sD[i + 1];
-                        float p0 = exp2f((s[nt][0] * 0.125f + ma - li) * LOG2E);  // (key x0, query i)
-                        float p1 = exp2f((s[nt][1] * 0.125f + ma - lj) * LOG2E);  // (key x0, query i+1)
-                        float p2 = exp2f((s[nt][2] * 0.125f + mb - li) * LOG2E);  // (key x1, query i)
-                        float p3 = exp2f((s[nt][3] * 0.125f + mb - lj) * LOG2E);  // (key x1, query i+1)
-                        if (i >= L) { p0 = 0.f; p2 = 0.f; }  // padded query rows: zero Q/dO, lse = 0
-                        if (i + 1 >= L) { p1 = 0.f; p3 = 0.f; }
-                        float k0 = 1.f, k1 = 1.f, k2 = 1.f, k3 = 1.f;
-                        if (drop.thresh16) {
-                            const uint32_t ba = (uint32_t)((bh * L + i) * Lh);
-                            const uint32_t bb = ba + (uint32_t)Lh;
-                            const uint32_t ha0 = attn_rng(key, ba + ((uint32_t)x0 >> 1));
-                            const uint32_t hb0 = attn_rng(key, bb + ((uint32_t)x0 >> 1));
-                            const uint32_t ha1 = attn_rng(key, ba + ((uint32_t)x1 >> 1));
-                            const uint32_t hb1 = attn_rng(key, bb + ((uint32_t)x1 >> 1));
-                            const int sh0 = (x0 & 1) * 16, sh1 = (x1 & 1) * 16;
-                            k0 = (((ha0 >> sh0) & 0xffffu) >= drop.thresh16) ? drop.scale : 0.f;
-                            k1 = (((hb0 >> sh0) & 0xffffu) >= drop.thresh16) ? drop.scale : 0.f;
-                            k2 = (((ha1 >> sh1) & 0xffffu) >= drop.thresh16) ? drop.scale : 0.f;
-                            k3 = (((hb1 >> sh1) & 0xffffu) >= drop.thresh16) ? drop.scale : 0.f;
-                        }
-                        pd[e][0] = p0 * k0; pd[e][1] = p1 * k1; pd[e][2] = p2 * k2; pd[e][3] = p3 * k3;
-                        ds[e][0] = p0 * (dp[nt][0] * k0 - Di) * 0.125f;
-                        ds[e][1] = p1 * (dp[nt][1] * k1 - Dj) * 0.125f;
-                        ds[e][2] = p2 * (dp[nt][2] * k2 - Di) * 0.125f;
-                        ds[e][3] = p3 * (dp[nt][3] * k3 - Dj) * 0.125f;
-                    }
-                    mma_x(dv, pack_bf16(pd[0][0], pd[0][1]), pack_bf16(pd[0][2], pd[0][3]),
-                          pack_bf16(pd[1][0], pd[1][1]), pack_bf16(pd[1][2], pd[1][3]), F1, c0 + np * 16, lane);
-                    mma_x(dk, pack_bf16(ds[0][0], ds[0][1]), pack_bf16(ds[0][2], ds[0][3]),
-                          pack_bf16(ds[1][0], ds[1][1]), pack_bf16(ds[1][2], ds[1][3]), F0, c0 + np * 16, lane);
-                }
-            }
-        }
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-            if (x0 < L) {
-                *reinterpret_cast<uint32_t*>(dbase + (size_t)x0 * ld + H + nt * 8 + t2) = pack_bf16(dk[nt][0], dk[nt][1]);
-                *reinterpret_cast<uint32_t*>(dbase + (size_t)x0 * ld + 2 * H + nt * 8 + t2) = pack_bf16(dv[nt][0], dv[nt][1]);
-            }
-            if (x1 < L) {
-                *reinterpret_cast<uint32_t*>(dbase + (size_t)x1 * ld + H + nt * 8 + t2) = pack_bf16(dk[nt][2], dk[nt][3]);
-                *reinterpret_cast<uint32_t*>(dbase + (size_t)x1 * ld + 2 * H + nt * 8 + t2) = pack_bf16(dv[nt][2], dv[nt][3]);
-            }
+        if (x1 < L) {
+            *reinterpret_cast<uint32_t*>(dbase + (size_t)x1 * ld + H + nt * 8 + t2) = pack_bf16(dk[nt][2], dk[nt][3]);
+            *reinterpret_cast<uint32_t*>(dbase + (size_t)x1 * ld + 2 * H + nt * 8 + t2) = pack_bf16(dv[nt][2], dv[nt][3]);
         }
     }
 }
@@ -466,17 +459,27 @@ static int launch_fwd(const void* qkv, const float* mask, void* ctx, float* lse,
 }
 
 static int launch_bwd(const void* qkv, const float* mask, const void* ctx, const void* dctx,
-                      const float* lse, void* dqkv, int B, int L, int nh, int H, DropoutCfg dc,
-                      cudaStream_t stream) {
+                      const float* lse, void* dqkv, void* scratch, int B, int L, int nh, int H,
+                      DropoutCfg dc, cudaStream_t stream) {
     const int LP = (L + 15) / 16 * 16;
-    const size_t smem = (size_t)(2 * LP + 2 * TQ) * HD * 2 + (size_t)3 * LP * 4;
-    static size_t set_for = 0;
-    if (smem > set_for) {
-        B200U_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        set_for = smem;
+    bf16* scrP = (bf16*)scratch;
+    bf16* scrS = scrP + (size_t)B * nh * L * LP;
+    const size_t smem1 = (size_t)(2 * LP + 2 * TQ) * HD * 2 + (size_t)(LP + 2 * TQ) * 4;
+    const size_t smem2 = (size_t)4 * LP * HD * 2;
+    static size_t set1 = 0, set2 = 0;
+    if (smem1 > set1) {
+        B200U_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+        set1 = smem1;
     }
-    attn_bwd_kernel<<<dim3(B * nh, (L + TQ - 1) / TQ, 2), 128, smem, stream>>>((const bf16*)qkv, mask, (const bf16*)ctx, (const bf16*)dctx, lse, (bf16*)dqkv, L, LP, nh, H, dc);
-    B200U_CHECK_LAUNCH("attn_bwd_kernel");
+    if (smem2 > set2) {
+        B200U_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+        set2 = smem2;
+    }
+    const dim3 grid(B * nh, (L + TQ - 1) / TQ);
+    attn_bwd_dq_kernel<<<grid, 128, smem1, stream>>>((const bf16*)qkv, mask, (const bf16*)ctx, (const bf16*)dctx, lse, (bf16*)dqkv, scrP, scrS, L, LP, nh, H, dc);
+    B200U_CHECK_LAUNCH("attn_bwd_dq_kernel");
+    attn_bwd_dkv_kernel<<<grid, 128, smem2, stream>>>((const bf16*)qkv, (const bf16*)dctx, scrP, scrS, (bf16*)dqkv, L, LP, nh, H);
+    B200U_CHECK_LAUNCH("attn_bwd_dkv_kernel");
     return B200U_OK;
 }
 
@@ -497,16 +500,21 @@ extern "C" int b200u_attention_fwd(const void* qkv, const float* mask, void* ctx
     return launch_fwd(qkv, mask, ctx, lse, B, L, num_heads, H, dc, stream);
 }
 
+extern "C" size_t b200u_attention_bwd_scratch_bytes(int B, int L, int num_heads) {
+    const size_t LP = (size_t)(L + 15) / 16 * 16;
+    return (size_t)2 * B * num_heads * L * LP * sizeof(bf16);
+}
+
 extern "C" int b200u_attention_bwd(const void* qkv, const float* mask, const void* ctx,
-                                   const void* dctx, const float* lse, void* dqkv, int B, int L,
-                                   int num_heads, int H, const b200u_dropout_t* drop,
+                                   const void* dctx, const float* lse, void* dqkv, void* scratch, int B,
+                                   int L, int num_heads, int H, const b200u_dropout_t* drop,
                                    b200u_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
-    B200U_CHECK_ARG(qkv && mask && ctx && dctx && lse && dqkv, "attention_bwd: null pointer");
+    B200U_CHECK_ARG(qkv && mask && ctx && dctx && lse && dqkv && scratch, "attention_bwd: null pointer");
     B200U_CHECK_ARG(num_heads > 0 && H == num_heads * HD, "attention_bwd: head dim must be 64 (H=%d heads=%d)", H, num_heads);
     B200U_CHECK_ARG(L > 0 && L <= 256, "attention_bwd: joint sequence length %d unsupported (1..256)", L);
     if (B == 0) return B200U_OK;
     DropoutCfg dc = make_drop(drop);
     B200U_CHECK_ARG(dc.thresh16 == 0 || dc.seed_ptr, "attention_bwd: dropout needs seed_ptr");
-    return launch_bwd(qkv, mask, ctx, dctx, lse, dqkv, B, L, num_heads, H, dc, stream);
+    return launch_bwd(qkv, mask, ctx, dctx, lse, dqkv, scratch, B, L, num_heads, H, dc, stream);
 }

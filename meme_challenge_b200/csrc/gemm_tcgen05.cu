@@ -202,7 +202,9 @@ struct GemmCfg {
     static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
     static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int STG_PER_WARP = 4096 * (DUAL ? 2 : 1);
+    // epilogues with a side-input tile write their result over it in place (same swizzled slot),
+    // so they need no separate staging buffer
+    static constexpr int STG_PER_WARP = HAS_R ? 0 : 4096 * (DUAL ? 2 : 1);
     static constexpr int STG_BYTES = EPI_WARPS * STG_PER_WARP;
     static constexpr int R_BYTES = HAS_R ? BLOCK_M * BLOCK_N * 2 : 0;
     static constexpr int BIAS_BYTES = EPI_WARPS * BLOCK_N * 4;
@@ -505,8 +507,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     tmem_ld_32x32(taddr + col0, r0);
                     tmem_ld_32x32(taddr + col0 + 32, r1);
                     tmem_ld_wait();
-                    if (lane == 0) bulk_wait_read_all();
-                    __syncwarp();
+                    uint8_t* dst = Cfg::HAS_R ? sR + gi * (BLOCK_M * 128) + q * (32 * 128) : stg;
+                    if (!Cfg::HAS_R) {
+                        if (lane == 0) bulk_wait_read_all();  // staging buffer free again?
+                        __syncwarp();
+                    }
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         float v[8], w[8];
@@ -520,7 +525,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         uint4 o;
                         o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]);
                         o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
-                        *reinterpret_cast<uint4*>(stg + lane * 128 + ((j ^ sw) << 4)) = o;
+                        *reinterpret_cast<uint4*>(dst + lane * 128 + ((j ^ sw) << 4)) = o;
                         if (Cfg::DUAL) {
                             uint4 o2;
                             o2.x = pack_bf16(w[0], w[1]); o2.y = pack_bf16(w[2], w[3]);
@@ -531,7 +536,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     fence_proxy_async();
                     __syncwarp();
                     if (lane == 0) {
-                        tma_store_2d(&tmC, stg, n0 + col0, m0 + q * 32);
+                        tma_store_2d(&tmC, dst, n0 + col0, m0 + q * 32);
                         if (Cfg::DUAL) tma_store_2d(&tmC2, stg + 4096, n0 + col0, m0 + q * 32);
                         bulk_commit();
                     }
@@ -541,7 +546,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             __syncwarp();
             if (lane == 0) {
                 mbar_arrive(&tempty[as]);
-                if (Cfg::HAS_R) mbar_arrive(rempty);
+                if (Cfg::HAS_R) {
+                    bulk_wait_read_all();  // the TMA stores have finished reading the side-input tile
+                    mbar_arrive(rempty);
+                }
             }
             rph ^= 1;
             as ^= 1;
@@ -776,10 +784,8 @@ extern "C" int b200u_gemm(const b200u_gemm_t* d, b200u_stream_t stream_) {
         const int t256 = m_tiles * ((d->N + 255) / 256);
         block_n = (d->N >= 256 && t256 >= num_sms()) ? 256 : 128;
     }
-    // epilogues that stage a side-input tile in smem keep 128-wide tiles (>= 4 pipeline stages)
-    if (d->block_n == 0 && (d->epilogue == B200U_EPI_BIAS_DROP_RES || d->epilogue == B200U_EPI_ADD ||
-                            d->epilogue == B200U_EPI_DGELU))
-        block_n = 128;
+    // (epilogues with a side-input tile keep it in smem and write their output over it in place:
+    //  3 pipeline stages remain at 256-wide tiles, 5 at 128)
     int splits = d->splits;
     if (d->epilogue != B200U_EPI_ATOMIC_F32) splits = 1;
     else if (splits <= 0) {

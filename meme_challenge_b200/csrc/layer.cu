@@ -117,7 +117,7 @@ extern "C" int b200u_bert_layer_bwd(const b200u_layer_params_t* p, const void* x
              nullptr, 0, nullptr, impl, st));
     TRY(gemm(M, H, H, dz1, H, 0, p->Wo, H, 1, B200U_EPI_STORE, w->dctx, H, nullptr, 0, nullptr, nullptr, 0,
              nullptr, impl, st));
-    TRY(b200u_attention_bwd(s->qkv, p->mask, s->ctx, w->dctx, s->lse, w->dqkv, p->B, p->L, p->heads, H,
+    TRY(b200u_attention_bwd(s->qkv, p->mask, s->ctx, w->dctx, s->lse, w->dqkv, w->attn, p->B, p->L, p->heads, H,
                             &d_attn, st));
     TRY(b200u_colsum_accum(w->dqkv, 3 * H, g->dbqkv, M, 3 * H, st));
     // QKV projection: dWqkv[3H,H] += dqkvᵀ·x0 ; dx0 = dqkv·Wqkv + dres

@@ -73,7 +73,7 @@ class LayerGradsT(C.Structure):
 
 
 class LayerScratchT(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in ("dres", "dz", "dx1", "dctx", "du", "dqkv")]
+    _fields_ = [(n, C.c_void_p) for n in ("dres", "dz", "dx1", "dctx", "du", "dqkv", "attn")]
 
 
 def _layer_params(layer, rt, B, L, mask_add, layer_idx):
@@ -149,8 +149,8 @@ def _alloc_saved(M, H, I, B, heads, L, dev):
 _scratch_cache = {}
 
 
-def _scratch(M, H, I, dev):
-    key = (M, H, I, dev.index, torch.cuda.is_current_stream_capturing())
+def _scratch(M, H, I, dev, B=0, L=0, heads=0):
+    key = (M, H, I, B, L, heads, dev.index, torch.cuda.is_current_stream_capturing())
     hit = _scratch_cache.get(key)
     if hit is None:
         buf = torch.empty(M * (4 * H + I + 3 * H), device=dev, dtype=torch.bfloat16)
@@ -160,7 +160,9 @@ def _scratch(M, H, I, dev):
                         ("dqkv", M * 3 * H)):
             setattr(w, name, buf[o:o + n].data_ptr())
             o += n
-        hit = (w, buf)
+        attn = torch.empty(_lib.lib().b200u_attention_bwd_scratch_bytes(B, L, heads), device=dev, dtype=torch.uint8)
+        w.attn = attn.data_ptr()
+        hit = (w, buf, attn)
         if len(_scratch_cache) > 8:
             _scratch_cache.clear()
         _scratch_cache[key] = hit
@@ -192,7 +194,7 @@ class BertLayerFn(torch.autograd.Function):
         p, rt = ctx.p, ctx.rt
         dx2 = dx2.contiguous()
         g = _layer_grads(ctx.layer, rt.store)
-        w = _scratch(p.B * p.L, p.H, p.I, x0.device)
+        w = _scratch(p.B * p.L, p.H, p.I, x0.device, p.B, p.L, p.heads)
         dx0 = torch.empty_like(x0)
         _lib.check(_lib.lib().b200u_bert_layer_bwd(C.byref(p), P(x0), C.byref(ctx.saved), P(dx2),
                                                    C.byref(g), C.byref(w), P(dx0), _lib.stream_ptr()),

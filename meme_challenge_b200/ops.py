@@ -138,7 +138,9 @@ def attention_fwd(qkv, mask, B, L, heads, H, drop=None, want_lse=True):
 
 def attention_bwd(qkv, mask, ctx, dctx, lse, B, L, heads, H, drop=None):
     dqkv = torch.empty_like(qkv)
-    _call("b200u_attention_bwd", P(qkv), P(mask), P(ctx), P(dctx), P(lse), P(dqkv), B, L, heads, H,
+    nbytes = _lib.lib().b200u_attention_bwd_scratch_bytes(B, L, heads)
+    scratch = torch.empty(nbytes, device=qkv.device, dtype=torch.uint8)
+    _call("b200u_attention_bwd", P(qkv), P(mask), P(ctx), P(dctx), P(lse), P(dqkv), P(scratch), B, L, heads, H,
           _drop_ref(drop))
     return dqkv
 

@@ -14,7 +14,7 @@ def _header_functions():
     hdr = open(os.path.join(ROOT, "include", "b200u.h")).read()
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
     out = {}
-    for m in re.finditer(r"\b(?:int|long long|const char\*)\s+(b200u_[a-z0-9_]+)\s*\(([^;]*?)\)\s*;", hdr, re.S):
+    for m in re.finditer(r"\b(?:int|long long|size_t|const char\*)\s+(b200u_[a-z0-9_]+)\s*\(([^;]*?)\)\s*;", hdr, re.S):
         args = m.group(2).strip()
         out[m.group(1)] = 0 if args in ("", "void") else len(args.split(","))
     return out
