@@ -83,16 +83,26 @@ __device__ __forceinline__ void mma_x(float (&o)[8][4], uint32_t a0, uint32_t a1
     }
 }
 
-// cooperative load of `rows` rows x 64 bf16 from a [*, ld] matrix into a swizzled smem tile,
-// zero-filling rows >= valid.
+// cooperative ASYNC load (cp.async, 16 B per request, all requests in flight at once) of `rows` rows
+// x 64 bf16 from a [*, ld] matrix into a swizzled smem tile, zero-filling rows >= valid. Callers
+// finish with load_tiles_wait() before the __syncthreads() that publishes the tiles.
 __device__ __forceinline__ void load_tile(bf16* dst, const bf16* src, int ld, int valid, int rows,
-                                          int tid, int nthreads) {
+                                          int tid, int nthreads, int valid_chunks = 8) {
     for (int i = tid; i < rows * 8; i += nthreads) {
         const int r = i >> 3, ch = i & 7;
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (r < valid) v = *reinterpret_cast<const uint4*>(src + (size_t)r * ld + ch * 8);
-        *reinterpret_cast<uint4*>(dst + sw_off(r, ch)) = v;
+        bf16* d = dst + sw_off(r, ch);
+        if (r < valid && ch < valid_chunks) {
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(d)),
+                         "l"(src + (size_t)r * ld + ch * 8)
+                         : "memory");
+        } else {
+            *reinterpret_cast<uint4*>(d) = make_uint4(0, 0, 0, 0);
+        }
     }
+}
+__device__ __forceinline__ void load_tiles_wait() {
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 // Attention-probability dropout uses a one-round keyed hash (the score matrix is the largest
@@ -131,6 +141,7 @@ attn_fwd_kernel(const bf16* __restrict__ qkv, const float* __restrict__ mask, bf
     load_tile(sK, base + H, ld, L, LP, tid, 128);
     load_tile(sV, base + 2 * H, ld, L, LP, tid, 128);
     for (int j = tid; j < LP; j += 128) sM[j] = (j < L) ? mask[(size_t)b * L + j] : -INFINITY;
+    load_tiles_wait();
     __syncthreads();
 
     const int r0 = q0 + warp * 16;
@@ -281,6 +292,7 @@ attn_bwd_dq_kernel(const bf16* __restrict__ qkv, const float* __restrict__ mask,
             sL2[i] = (gi < L) ? lse[(size_t)bh * L + gi] * LOG2E : 0.f;
         }
     }
+    load_tiles_wait();
     __syncthreads();
 
     const int r0 = t0 + warp * 16;
@@ -395,16 +407,10 @@ attn_bwd_dkv_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dctx,
     load_tile(sQ, base, ld, L, LP, tid, 128);
     load_tile(sdO, dO, H, L, LP, tid, 128);
     // key columns t0..t0+63 of every query row; columns >= LP (last tile) are zero-filled
-    for (int i = tid; i < LP * 8; i += 128) {
-        const int r = i >> 3, ch = i & 7;
-        uint4 vp = make_uint4(0, 0, 0, 0), vs = make_uint4(0, 0, 0, 0);
-        if (r < L && t0 + ch * 8 < LP) {
-            vp = *reinterpret_cast<const uint4*>(scrP + ((size_t)bh * L + r) * LP + t0 + ch * 8);
-            vs = *reinterpret_cast<const uint4*>(scrS + ((size_t)bh * L + r) * LP + t0 + ch * 8);
-        }
-        *reinterpret_cast<uint4*>(sP + sw_off(r, ch)) = vp;
-        *reinterpret_cast<uint4*>(sS + sw_off(r, ch)) = vs;
-    }
+    const int vch = min(8, (LP - t0) >> 3);
+    load_tile(sP, scrP + (size_t)bh * L * LP + t0, LP, L, LP, tid, 128, vch);
+    load_tile(sS, scrS + (size_t)bh * L * LP + t0, LP, L, LP, tid, 128, vch);
+    load_tiles_wait();
     __syncthreads();
     const int r0 = t0 + warp * 16;
     if (r0 >= L) return;
