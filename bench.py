@@ -200,8 +200,14 @@ def run_b200(args, rank, world, local_rank):
     torch.manual_seed(0)
     cfg = UniterConfig.from_dict(BASE)
     model = MemeUniter(UniterModel(cfg, 2048), 768, 1).to(dev).train()
+    # data-parallel modes (N > 1): "graph-overlap" captures the step INCLUDING the hook-issued NCCL bucket
+    # all-reduces (forked onto the process group's stream); "graph" captures blocking collectives on the
+    # compute stream (no overlap); "eager" launches everything from Python. auto = first that captures.
+    dp_modes = ["graph-overlap", "graph", "eager"] if args.dp_mode == "auto" else [args.dp_mode]
+    if world == 1:
+        dp_modes = ["eager"] if args.no_graph else ["graph", "eager"]
     ts = TrainStep(model, lr=3e-5, weight_decay=1e-3, gradient_accumulation=ACCUM, max_grad_norm=5.0, pos_wt=1.8,
-                   overlap_comm=not args.graph_dp)
+                   overlap_comm=True)
 
     # synthetic data: a ring of distinct host batches (pinned) and their device copies
     n_sets = 4
@@ -220,21 +226,38 @@ def run_b200(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- capture the whole optimizer step in a CUDA graph (falls back to eager on failure)
-    # N > 1: the overlapped NCCL bucket all-reduces are issued from autograd hooks, which cannot be
-    # stream-captured; data-parallel runs therefore execute the same TrainStep eagerly.
-    use_graph = (not args.no_graph) and (world == 1 or args.graph_dp)
+    # ---- capture the whole optimizer step in a CUDA graph (falls back mode by mode on failure; all
+    # ranks take the same decision: a failure on any rank moves every rank to the next mode)
+    use_graph = False
     launches_per_step = None
-    if use_graph:
+    dp_mode = "eager"
+    for mode in dp_modes:
+        dp_mode = mode
+        if mode == "eager":
+            ts.overlap_comm = True
+            ts.comm.sync = False
+            break
+        ts.overlap_comm = (mode == "graph-overlap")
+        ts.comm.sync = not ts.overlap_comm
+        ok = 1
         try:
             before = L.b200u_launch_count()
             ts.capture(devb[:ACCUM], warmup=2)
             launches_per_step = (L.b200u_launch_count() - before) // 3  # 2 warm-ups + 1 capture
         except Exception as e:  # noqa: BLE001
-            if rank == 0:
-                sys.stderr.write("CUDA graph capture failed (%s); running eager\n" % e)
-            use_graph = False
+            ok = 0
+            sys.stderr.write("[rank %d] CUDA graph capture in mode %s failed: %s\n" % (rank, mode, str(e)[:300]))
+            ts._graph = None
+            ts.comm.pending = []
+            ts.comm.reduced = []
             torch.cuda.synchronize()
+        if world > 1:
+            flag = torch.tensor([ok], device=dev, dtype=torch.int32)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            ok = int(flag.item())
+        if ok:
+            use_graph = True
+            break
     if launches_per_step is None:
         before = L.b200u_launch_count()
         ts.step(devb[:ACCUM])
@@ -320,7 +343,7 @@ def run_b200(args, rank, world, local_rank):
                 "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "global_batch": B * world, "grad_accum": ACCUM,
                            "memes_per_step": ACCUM * B * world, "parallelism": "dp%d" % world,
-                           "cuda_graph": use_graph,
+                           "cuda_graph": use_graph, "dp_mode": dp_mode if world > 1 else None,
                            "l2": "per-step working set (~0.75 GB saved activations + 1.5 GB fp32 params/grads/Adam "
                                  "state + 0.2 GB bf16 weights) exceeds the 126 MB L2; inputs rotate over %d batch sets" % n_sets,
                            "model_tflop_per_s": round(value * GFLOP_PER_MEME / 1e3, 1),
@@ -344,7 +367,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
-    ap.add_argument("--graph-dp", action="store_true", help="experimental: CUDA-graph the DP step (no comm overlap)")
+    ap.add_argument("--dp-mode", default="auto", choices=["auto", "graph-overlap", "graph", "eager"],
+                    help="N > 1: how the data-parallel step is launched (auto = first mode that captures)")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup)
     rank = int(os.environ.get("RANK", "0"))

@@ -34,6 +34,11 @@ int b200u_version(void);
 int b200u_device_info(int* sm_count, int* cc_major, int* cc_minor);
 /* Number of kernels this library has launched in the process so far (bench.py gpu_launches). */
 long long b200u_launch_count(void);
+/* Programmatic dependent launch (default on): every kernel of the library is launched with
+ * cudaLaunchAttributeProgrammaticStreamSerialization and calls griddepcontrol.wait before its
+ * first global-memory access, so its launch + prologue overlap the tail of the preceding kernel
+ * on the stream (also inside captured CUDA graphs). 0 turns the attribute off. */
+int b200u_set_pdl(int on);
 /* Event-time every tcgen05 GEMM launch (bench.py roofline leg). enable(n) arms up to n records,
  * collect() synchronises and returns summed duration / algorithmic FLOPs (2MNK) / record count.
  * Must not be armed during CUDA-graph capture. */

@@ -18,6 +18,7 @@ SIGNATURES = {
     "b200u_version": (_i, []),
     "b200u_device_info": (_i, [C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
     "b200u_launch_count": (_ll, []),
+    "b200u_set_pdl": (_i, [_i]),
     "b200u_prof_enable": (_i, [_i]),
     "b200u_prof_collect": (_i, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_i)]),
     "b200u_gemm": (_i, [_p, _p]),

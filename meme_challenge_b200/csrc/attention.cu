@@ -125,6 +125,7 @@ constexpr float LOG2E = 1.4426950408889634f;
 __global__ void __launch_bounds__(128, 4)
 attn_fwd_kernel(const bf16* __restrict__ qkv, const float* __restrict__ mask, bf16* __restrict__ ctx,
                 float* __restrict__ lse, int L, int LP, int nh, int H, DropoutCfg drop) {
+    pdl_sync();
     extern __shared__ __align__(128) uint8_t smem_raw[];
     bf16* sK = reinterpret_cast<bf16*>(smem_raw);
     bf16* sV = sK + LP * HD;
@@ -247,6 +248,7 @@ attn_bwd_dq_kernel(const bf16* __restrict__ qkv, const float* __restrict__ mask,
                    const bf16* __restrict__ ctx, const bf16* __restrict__ dctx,
                    const float* __restrict__ lse, bf16* __restrict__ dqkv, bf16* __restrict__ scrP,
                    bf16* __restrict__ scrS, int L, int LP, int nh, int H, DropoutCfg drop) {
+    pdl_sync();
     extern __shared__ __align__(128) uint8_t smem_raw[];
     bf16* sK = reinterpret_cast<bf16*>(smem_raw);
     bf16* sV = sK + LP * HD;
@@ -392,6 +394,7 @@ __global__ void __launch_bounds__(128, 3)
 attn_bwd_dkv_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dctx,
                     const bf16* __restrict__ scrP, const bf16* __restrict__ scrS,
                     bf16* __restrict__ dqkv, int L, int LP, int nh, int H) {
+    pdl_sync();
     extern __shared__ __align__(128) uint8_t smem_raw[];
     bf16* sQ = reinterpret_cast<bf16*>(smem_raw);  // [LP][64]
     bf16* sdO = sQ + LP * HD;                      // [LP][64]
@@ -459,7 +462,7 @@ static int launch_fwd(const void* qkv, const float* mask, void* ctx, float* lse,
         B200U_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         set_for = smem;
     }
-    attn_fwd_kernel<<<dim3(B * nh, (L + TQ - 1) / TQ), 128, smem, stream>>>((const bf16*)qkv, mask, (bf16*)ctx, lse, L, LP, nh, H, dc);
+    launch_k(attn_fwd_kernel, dim3(dim3(B * nh, (L + TQ - 1) / TQ)), dim3(128), smem, stream, (const bf16*)qkv, mask, (bf16*)ctx, lse, L, LP, nh, H, dc);
     B200U_CHECK_LAUNCH("attn_fwd_kernel");
     return B200U_OK;
 }
@@ -482,9 +485,9 @@ static int launch_bwd(const void* qkv, const float* mask, const void* ctx, const
         set2 = smem2;
     }
     const dim3 grid(B * nh, (L + TQ - 1) / TQ);
-    attn_bwd_dq_kernel<<<grid, 128, smem1, stream>>>((const bf16*)qkv, mask, (const bf16*)ctx, (const bf16*)dctx, lse, (bf16*)dqkv, scrP, scrS, L, LP, nh, H, dc);
+    launch_k(attn_bwd_dq_kernel, dim3(grid), dim3(128), smem1, stream, (const bf16*)qkv, mask, (const bf16*)ctx, (const bf16*)dctx, lse, (bf16*)dqkv, scrP, scrS, L, LP, nh, H, dc);
     B200U_CHECK_LAUNCH("attn_bwd_dq_kernel");
-    attn_bwd_dkv_kernel<<<grid, 128, smem2, stream>>>((const bf16*)qkv, (const bf16*)dctx, scrP, scrS, (bf16*)dqkv, L, LP, nh, H);
+    launch_k(attn_bwd_dkv_kernel, dim3(grid), dim3(128), smem2, stream, (const bf16*)qkv, (const bf16*)dctx, scrP, scrS, (bf16*)dqkv, L, LP, nh, H);
     B200U_CHECK_LAUNCH("attn_bwd_dkv_kernel");
     return B200U_OK;
 }

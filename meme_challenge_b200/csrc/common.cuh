@@ -55,6 +55,28 @@ void count_launch();  // bumps the kernel-launch counter read by b200u_launch_co
 bool prof_begin(cudaStream_t st, double flops, int* slot);
 void prof_end(cudaStream_t st, int slot);
 int num_sms();  // cached cudaDevAttrMultiProcessorCount of the current device
+bool pdl_enabled();  // b200u_set_pdl(): launch kernels with programmatic stream serialization
+
+// Every kernel of the library is launched through launch_k(): with PDL on, the launch carries
+// cudaLaunchAttributeProgrammaticStreamSerialization, so its CTAs may become resident (and run
+// their prologue up to pdl_wait()) while the preceding kernel on the stream is still draining.
+// Contract: every kernel calls pdl_wait() before its first global-memory access (read OR write)
+// and before any early return, then pdl_launch() so its own successor can be scheduled.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                            cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 
 typedef __nv_bfloat16 bf16;
 typedef __nv_bfloat162 bf162;
@@ -89,12 +111,21 @@ __device__ __forceinline__ uint64_t load_seed(const DropoutCfg& d) {
     return d.thresh16 ? *d.seed_ptr : 0ull;
 }
 
+// Programmatic dependent launch (see launch_k above). No-ops when launched without the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_sync() {
+    pdl_wait();
+    pdl_launch();
+}
+
 // ---------------------------------------------------------------------------------------
 // Small math helpers (reference: model/layer.py:31-37 exact erf GELU).
 // ---------------------------------------------------------------------------------------
 // erf via Abramowitz-Stegun 7.1.26 (|abs error| <= 1.5e-7, i.e. fp32-level for GELU): one
-// reciprocal, one exp2 and five FMAs instead of erff()'s ~40-instruction polynomial, so the fused
-// GEMM epilogues stay cheaper than the main loop they overlap with.
+// reciprocal, one exp2 and a handful of FMAs instead of erff()'s ~40-instruction polynomial,
+// evaluated on element PAIRS with packed fp32x2 instructions so the fused GEMM epilogues stay
+// cheaper than the main loop they overlap with.
 __device__ __forceinline__ float rcp_approx(float x) {  // MUFU.RCP, callers guarantee x >= 1
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
@@ -105,23 +136,97 @@ __device__ __forceinline__ float ex2_approx(float x) {  // MUFU.EX2
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
-__device__ __forceinline__ float erf_fast(float x) {
-    const float ax = fabsf(x);
-    const float t = rcp_approx(fmaf(0.3275911f, ax, 1.0f));
-    float p = fmaf(1.061405429f, t, -1.453152027f);
-    p = fmaf(p, t, 1.421413741f);
-    p = fmaf(p, t, -0.284496736f);
-    p = fmaf(p, t, 0.254829592f);
-    const float e = ex2_approx(-1.4426950408889634f * ax * ax);
-    return copysignf(fmaf(-p * t, e, 1.0f), x);
+// ---- packed fp32x2 arithmetic (sm_100 FFMA2 / FMUL2 / FADD2: two fp32 lanes per issue slot) ----
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 f2(float lo, float hi) {
+    f32x2 d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
+    return d;
+}
+__device__ __forceinline__ f32x2 f2s(float c) { return f2(c, c); }
+__device__ __forceinline__ void f2_get(f32x2 v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 f2_fma(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ f32x2 f2_mul(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f32x2 f2_add(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+// two bf16 packed in a 32-bit word (low half = first element) <-> fp32 pair
+__device__ __forceinline__ f32x2 f2_from_bf16x2(uint32_t u) {
+    return f2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+}
+__device__ __forceinline__ uint32_t f2_to_bf16x2(f32x2 v) {
+    float lo, hi;
+    f2_get(v, lo, hi);
+    uint32_t d;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+
+// q = erfc(a * s / sqrt 2) for a >= 0 via Abramowitz-Stegun 7.1.26 (|abs error| <= 1.5e-7) and
+// e = exp(-(a s)^2 / 2), on a PAIR of values: 2 MUFU.RCP + 2 MUFU.EX2 + 8 packed FMA/MUL.
+// `a` is |x| pre-scaled by 1/s (the GELU forward passes |x|/2, so s = 2).
+template <int S>
+__device__ __forceinline__ f32x2 erfc_pair(f32x2 a, f32x2& e) {
+    const f32x2 d = f2_fma(a, f2s(0.3275911f * 0.70710678118654752440f * S), f2s(1.0f));
+    float d0, d1;
+    f2_get(d, d0, d1);
+    const f32x2 t = f2(rcp_approx(d0), rcp_approx(d1));
+    f32x2 p = f2_fma(t, f2s(1.061405429f), f2s(-1.453152027f));
+    p = f2_fma(p, t, f2s(1.421413741f));
+    p = f2_fma(p, t, f2s(-0.284496736f));
+    p = f2_fma(p, t, f2s(0.254829592f));
+    const f32x2 s = f2_mul(f2_mul(a, a), f2s(-0.72134752044448170368f * S * S));
+    float s0, s1;
+    f2_get(s, s0, s1);
+    e = f2(ex2_approx(s0), ex2_approx(s1));
+    return f2_mul(f2_mul(p, t), e);
+}
+// gelu(x) = x/2 (1 + erf(x/sqrt 2)) = relu(x) - |x|/2 * erfc(|x|/sqrt 2)   (model/layer.py:31-37)
+__device__ __forceinline__ f32x2 gelu_pair(f32x2 x) {
+    const f32x2 h = f2_mul(x, f2s(0.5f));
+    float h0, h1;
+    f2_get(h, h0, h1);
+    const f32x2 ah = f2(fabsf(h0), fabsf(h1));
+    f32x2 e;
+    const f32x2 q = erfc_pair<2>(ah, e);
+    return f2_fma(f2_mul(ah, q), f2s(-1.0f), f2_add(h, ah));
+}
+// gelu'(x) = Phi(x) + x phi(x), Phi(x) = 1/2 + copysign(1/2 - erfc(|x|/sqrt 2)/2, x)
+__device__ __forceinline__ f32x2 gelu_grad_pair(f32x2 x) {
+    float x0, x1;
+    f2_get(x, x0, x1);
+    const f32x2 ax = f2(fabsf(x0), fabsf(x1));
+    f32x2 e;
+    const f32x2 q = erfc_pair<1>(ax, e);
+    const f32x2 hq = f2_fma(q, f2s(-0.5f), f2s(0.5f));  // in [0, 1/2]
+    float q0, q1;
+    f2_get(hq, q0, q1);
+    const f32x2 sg = f2(__uint_as_float(__float_as_uint(q0) | (__float_as_uint(x0) & 0x80000000u)),
+                        __uint_as_float(__float_as_uint(q1) | (__float_as_uint(x1) & 0x80000000u)));
+    const f32x2 cdf = f2_add(sg, f2s(0.5f));
+    return f2_fma(f2_mul(x, e), f2s(0.39894228040143267794f), cdf);
 }
 __device__ __forceinline__ float gelu_erf(float x) {
-    return x * 0.5f * (1.0f + erf_fast(x * 0.70710678118654752440f));
+    float lo, hi;
+    f2_get(gelu_pair(f2(x, x)), lo, hi);
+    return lo;
 }
 __device__ __forceinline__ float gelu_erf_grad(float x) {
-    float cdf = 0.5f * (1.0f + erf_fast(x * 0.70710678118654752440f));
-    float pdf = 0.39894228040143267794f * ex2_approx(-0.72134752044448170368f * x * x);
-    return cdf + x * pdf;
+    float lo, hi;
+    f2_get(gelu_grad_pair(f2(x, x)), lo, hi);
+    return lo;
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -73,6 +73,7 @@ txt_embed_fwd_kernel(const long long* __restrict__ ids, const long long* __restr
                      const float* __restrict__ beta, bf16* __restrict__ out, float* __restrict__ sum_out,
                      float* __restrict__ mean_out, float* __restrict__ rstd_out, int n, int T, int H,
                      float eps, DropoutCfg drop) {
+    pdl_sync();
     const int lane = threadIdx.x & 31;
     const int tok = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (tok >= n) return;
@@ -127,6 +128,7 @@ img_embed_fwd_kernel(const float* __restrict__ a, const float* __restrict__ pos7
                      const float* __restrict__ g, const float* __restrict__ be,
                      bf16* __restrict__ out, float* __restrict__ p_out, float* __restrict__ s_out,
                      float* __restrict__ stats_out, int n, int H, float eps, DropoutCfg drop) {
+    pdl_sync();
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= n) return;
@@ -200,6 +202,7 @@ __global__ void __launch_bounds__(256)
 embedding_scatter_add_kernel(const bf16* __restrict__ d, const long long* __restrict__ ids,
                              int ids_batch_stride, int T, long long const_id, float* __restrict__ table_grad,
                              int n, int H, long long padding_idx) {
+    pdl_sync();
     const int lane = threadIdx.x & 31;
     const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (r >= n) return;
@@ -226,6 +229,7 @@ embedding_scatter_add_kernel(const bf16* __restrict__ d, const long long* __rest
 __global__ void __launch_bounds__(256)
 pos_linear_wgrad_kernel(const bf16* __restrict__ dp, const float* __restrict__ pos7,
                         float* __restrict__ dW, int n, int H, int rows_per_block) {
+    pdl_sync();
     const int h = blockIdx.x * blockDim.x + threadIdx.x;
     const int r0 = blockIdx.y * rows_per_block;
     const int r1 = min(n, r0 + rows_per_block);
@@ -284,7 +288,7 @@ extern "C" int b200u_txt_embed_fwd(const long long* input_ids, const long long* 
     if (n == 0) return B200U_OK;
     DropoutCfg dc = make_drop(drop);
     B200U_CHECK_ARG(dc.thresh16 == 0 || dc.seed_ptr, "txt_embed_fwd: dropout needs seed_ptr");
-    txt_embed_fwd_kernel<<<(n + 7) / 8, 256, 0, stream>>>(input_ids, position_ids, pos_batch_stride, type_ids, word, pos, type, gamma, beta, (bf16*)out, sum_out, mean, rstd, n, T, H, eps, dc);
+    launch_k(txt_embed_fwd_kernel, dim3((n + 7) / 8), dim3(256), 0, stream, input_ids, position_ids, pos_batch_stride, type_ids, word, pos, type, gamma, beta, (bf16*)out, sum_out, mean, rstd, n, T, H, eps, dc);
     B200U_CHECK_LAUNCH("txt_embed_fwd");
     return B200U_OK;
 }
@@ -301,7 +305,7 @@ extern "C" int b200u_img_embed_fwd(const float* a, const float* pos7, const floa
     if (n == 0) return B200U_OK;
     DropoutCfg dc = make_drop(drop);
     B200U_CHECK_ARG(dc.thresh16 == 0 || dc.seed_ptr, "img_embed_fwd: dropout needs seed_ptr");
-    img_embed_fwd_kernel<<<(n + 7) / 8, 256, 0, stream>>>(a, pos7, Wpos, bpos, type_ids, type, g_img, b_img, g_pos, b_pos, g, b, (bf16*)out, p_out, s_out, stats_out, n, H, eps, dc);
+    launch_k(img_embed_fwd_kernel, dim3((n + 7) / 8), dim3(256), 0, stream, a, pos7, Wpos, bpos, type_ids, type, g_img, b_img, g_pos, b_pos, g, b, (bf16*)out, p_out, s_out, stats_out, n, H, eps, dc);
     B200U_CHECK_LAUNCH("img_embed_fwd");
     return B200U_OK;
 }
@@ -312,7 +316,7 @@ extern "C" int b200u_embedding_scatter_add(const void* d, const long long* ids, 
     cudaStream_t stream = (cudaStream_t)stream_;
     B200U_CHECK_ARG(d && table_grad && H % 8 == 0 && T > 0, "embedding_scatter_add: bad arguments");
     if (n == 0) return B200U_OK;
-    embedding_scatter_add_kernel<<<(n + 7) / 8, 256, 0, stream>>>((const bf16*)d, ids, ids_batch_stride, T, const_id, table_grad, n, H, padding_idx);
+    launch_k(embedding_scatter_add_kernel, dim3((n + 7) / 8), dim3(256), 0, stream, (const bf16*)d, ids, ids_batch_stride, T, const_id, table_grad, n, H, padding_idx);
     B200U_CHECK_LAUNCH("embedding_scatter_add");
     return B200U_OK;
 }
@@ -324,7 +328,7 @@ extern "C" int b200u_pos_linear_wgrad(const void* dp, const float* pos7, float* 
     if (n == 0) return B200U_OK;
     const int rows_per_block = 128;
     dim3 grid((H + 255) / 256, (n + rows_per_block - 1) / rows_per_block);
-    pos_linear_wgrad_kernel<<<grid, 256, 0, stream>>>((const bf16*)dp, pos7, dW, n, H, rows_per_block);
+    launch_k(pos_linear_wgrad_kernel, dim3(grid), dim3(256), 0, stream, (const bf16*)dp, pos7, dW, n, H, rows_per_block);
     B200U_CHECK_LAUNCH("pos_linear_wgrad");
     return B200U_OK;
 }

@@ -206,9 +206,10 @@ struct GemmCfg {
     // so they need no separate staging buffer
     static constexpr int STG_PER_WARP = HAS_R ? 0 : 4096 * (DUAL ? 2 : 1);
     static constexpr int STG_BYTES = EPI_WARPS * STG_PER_WARP;
-    static constexpr int R_BYTES = HAS_R ? BLOCK_M * BLOCK_N * 2 : 0;
-    static constexpr int BIAS_BYTES = EPI_WARPS * BLOCK_N * 4;
-    static constexpr int FIXED = 1024 /*align*/ + STG_BYTES + R_BYTES + BIAS_BYTES + 256 /*barriers*/;
+    static constexpr int R_GROUP_BYTES = BLOCK_M * 128;  // side input: one [128 x 64] bf16 box per group
+    static constexpr int R_BYTES = HAS_R ? NUM_GROUPS * R_GROUP_BYTES : 0;
+    static constexpr int BIAS_BYTES = 2 * BLOCK_N * 4;  // one slot per accumulator stage
+    static constexpr int FIXED = STG_BYTES + R_BYTES + BIAS_BYTES + 256 /*barriers*/;
     static constexpr int STAGES_RAW = (232448 - FIXED) / STAGE_BYTES;
     static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
     static_assert(STAGES >= 2, "not enough shared memory for a pipelined main loop");
@@ -216,45 +217,60 @@ struct GemmCfg {
     static constexpr int TMEM_COLS = 2 * BLOCK_N;  // two accumulator stages
 };
 
-// Epilogue math for 8 consecutive columns of one row (bf16 outputs).
+// Epilogue math for 8 consecutive columns of one row (bf16 outputs), on element pairs with packed
+// fp32x2 instructions. acc = 8 fp32 accumulators (bit patterns from tcgen05.ld); o = the 8 bf16
+// results; o2 = the second output of the dual-output GELU epilogue.
 template <int EPI>
-__device__ __forceinline__ void epi_math8(float (&v)[8], float (&w)[8], const float* bias8, uint4 rraw,
-                                          const GemmArgs& g, uint64_t seed, int row, int col) {
-    if (EPI == B200U_EPI_STORE || EPI == B200U_EPI_BIAS_GELU || EPI == B200U_EPI_BIAS_DROP_RES) {
+__device__ __forceinline__ void epi_math8(const uint32_t* acc, const float* bias8, uint4 rraw,
+                                          const GemmArgs& g, uint64_t seed, int row, int col,
+                                          uint4& o, uint4& o2) {
+    f32x2 v[4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] += bias8[i];
+    for (int i = 0; i < 4; ++i) v[i] = f2(__uint_as_float(acc[2 * i]), __uint_as_float(acc[2 * i + 1]));
+    if (EPI == B200U_EPI_STORE || EPI == B200U_EPI_BIAS_GELU || EPI == B200U_EPI_BIAS_DROP_RES) {
+        const float4 b0 = *reinterpret_cast<const float4*>(bias8);
+        const float4 b1 = *reinterpret_cast<const float4*>(bias8 + 4);
+        v[0] = f2_add(v[0], f2(b0.x, b0.y));
+        v[1] = f2_add(v[1], f2(b0.z, b0.w));
+        v[2] = f2_add(v[2], f2(b1.x, b1.y));
+        v[3] = f2_add(v[3], f2(b1.z, b1.w));
     }
-    float r[8];
-    if (EPI == B200U_EPI_BIAS_DROP_RES || EPI == B200U_EPI_ADD || EPI == B200U_EPI_DGELU) {
-        float2 f;
-        f = unpack_bf16(rraw.x); r[0] = f.x; r[1] = f.y;
-        f = unpack_bf16(rraw.y); r[2] = f.x; r[3] = f.y;
-        f = unpack_bf16(rraw.z); r[4] = f.x; r[5] = f.y;
-        f = unpack_bf16(rraw.w); r[6] = f.x; r[7] = f.y;
-    }
-    if (EPI == B200U_EPI_BIAS_DROP_RES) {
+    const uint32_t rr[4] = {rraw.x, rraw.y, rraw.z, rraw.w};
+    uint32_t out[4], out2[4] = {0u, 0u, 0u, 0u};
+    if (EPI == B200U_EPI_BIAS_GELU) {
+        // GELU of the bf16-rounded pre-activation: backward sees exactly the stored u.
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            out[i] = f2_to_bf16x2(v[i]);
+            out2[i] = f2_to_bf16x2(gelu_pair(f2_from_bf16x2(out[i])));
+        }
+    } else if (EPI == B200U_EPI_DGELU) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            out[i] = f2_to_bf16x2(f2_mul(v[i], gelu_grad_pair(f2_from_bf16x2(rr[i]))));
+    } else if (EPI == B200U_EPI_ADD) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) out[i] = f2_to_bf16x2(f2_add(v[i], f2_from_bf16x2(rr[i])));
+    } else if (EPI == B200U_EPI_BIAS_DROP_RES) {
         if (g.drop.thresh16) {
             const uint32_t pbase = (uint32_t)(((size_t)row * g.N + col) >> 1);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                uint32_t h = rng_pair(seed, g.drop.stream, pbase + i);
-                v[2 * i] = ((h & 0xffffu) >= g.drop.thresh16) ? v[2 * i] * g.drop.scale : 0.f;
-                v[2 * i + 1] = ((h >> 16) >= g.drop.thresh16) ? v[2 * i + 1] * g.drop.scale : 0.f;
+                const uint32_t h = rng_pair(seed, g.drop.stream, pbase + i);
+                const float m0 = ((h & 0xffffu) >= g.drop.thresh16) ? g.drop.scale : 0.f;
+                const float m1 = ((h >> 16) >= g.drop.thresh16) ? g.drop.scale : 0.f;
+                out[i] = f2_to_bf16x2(f2_fma(v[i], f2(m0, m1), f2_from_bf16x2(rr[i])));
             }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) out[i] = f2_to_bf16x2(f2_add(v[i], f2_from_bf16x2(rr[i])));
         }
+    } else {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] += r[i];
-    } else if (EPI == B200U_EPI_ADD) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] += r[i];
-    } else if (EPI == B200U_EPI_DGELU) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] *= gelu_erf_grad(r[i]);
-    } else if (EPI == B200U_EPI_BIAS_GELU) {
-        // GELU of the bf16-rounded pre-activation: backward sees exactly the stored u.
-#pragma unroll
-        for (int i = 0; i < 8; ++i) w[i] = gelu_erf(__bfloat162float(__float2bfloat16(v[i])));
+        for (int i = 0; i < 4; ++i) out[i] = f2_to_bf16x2(v[i]);
     }
+    o = make_uint4(out[0], out[1], out[2], out[3]);
+    o2 = make_uint4(out2[0], out2[1], out2[2], out2[3]);
 }
 
 // CLUSTER == 2: the two CTAs of a cluster work on vertically adjacent output tiles (same n-tile),
@@ -266,9 +282,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                const __grid_constant__ CUtensorMap tmR, const GemmArgs g) {
     using Cfg = GemmCfg<BLOCK_N, EPI>;
     constexpr int STAGES = Cfg::STAGES;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                               ~(uintptr_t)1023);
+    constexpr int NG = Cfg::NUM_GROUPS;
+    // 128B-swizzled TMA boxes need 1024-byte aligned shared memory: the dynamic window starts on a
+    // 1024-byte boundary when the kernel has no static shared memory (checked below).
+    extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* sA = smem;
     uint8_t* sB = sA + STAGES * Cfg::A_BYTES;
     uint8_t* sR = sB + STAGES * Cfg::B_BYTES;
@@ -278,13 +295,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint64_t* empty = full + STAGES;
     uint64_t* tfull = empty + STAGES;
     uint64_t* tempty = tfull + 2;
-    uint64_t* rfull = tempty + 2;
-    uint64_t* rempty = rfull + 1;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rempty + 1);
+    uint64_t* rfull = tempty + 2;   // [4] one per side-input group
+    uint64_t* rempty = rfull + 4;   // [4]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rempty + 4);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     if (threadIdx.x == 0) DBG_STAMP(0);
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
@@ -302,8 +320,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_init(&tfull[a], 1);
             mbar_init(&tempty[a], EPI_WARPS);
         }
-        mbar_init(rfull, 1);
-        mbar_init(rempty, EPI_WARPS);
+        for (int a = 0; a < 4; ++a) {
+            mbar_init(&rfull[a], 1);
+            mbar_init(&rempty[a], 4);  // the four quadrant warps that own this group
+        }
         fence_mbar_init();
     }
     if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
@@ -311,6 +331,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (CLUSTER > 1) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // everything above (barrier init, TMEM allocation, descriptor prefetch) overlaps the tail of
+    // the preceding kernel under programmatic dependent launch; global memory is touched from here
+    pdl_sync();
     if (threadIdx.x == 0) DBG_STAMP(1);
 
     // work units: (m-tile group of CLUSTER tiles, n-tile, k-split); a cluster walks units together
@@ -326,8 +349,41 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // ================= TMA producer =================
         if (lane == 0) {
             int s = 0;
-            uint32_t ph = 0, rph = 0;
+            uint32_t ph = 0;
+            // Side-input cursor: the next (tile, group) whose R box has not been requested. Boxes are
+            // requested opportunistically (try_wait on the group's empty barrier) from inside the
+            // operand loop and from its wait loops, never by blocking it: the epilogue that frees a
+            // group may itself be waiting, through the MMA warp, on operands only this thread loads.
+            int rt = unit0, rg = 0;
+            uint32_t rpar = 0;  // bit g: parity of the next use of group g's barriers
+            int t_cur = unit0;
+            int rm0 = 0, rn0 = 0;  // tile origin of the cursor (divisions only when the cursor moves)
+            auto r_origin = [&]() {
+                const int rrem = rt % tiles_mn;
+                rm0 = ((rrem % m_groups) * CLUSTER + cta_rank) * BLOCK_M;
+                rn0 = (rrem / m_groups) * BLOCK_N;
+            };
+            if (Cfg::HAS_R) r_origin();
+            auto r_pump = [&](bool block) {
+                if (!Cfg::HAS_R) return;
+                while (rt <= t_cur && rt < total_tiles) {
+                    if (rn0 + rg * 64 < g.N) {
+                        const uint32_t par = ((rpar >> rg) & 1u) ^ 1u;
+                        if (block) mbar_wait(&rempty[rg], par);
+                        else if (!mbar_try_wait(&rempty[rg], par)) return;
+                        mbar_arrive_expect_tx(&rfull[rg], Cfg::R_GROUP_BYTES);
+                        tma_load_2d(sR + rg * Cfg::R_GROUP_BYTES, &tmR, &rfull[rg], rn0 + 64 * rg, rm0);
+                        rpar ^= 1u << rg;
+                    }
+                    if (++rg == NG) {
+                        rg = 0;
+                        rt += unit_stride;
+                        r_origin();
+                    }
+                }
+            };
             for (int t = unit0; t < total_tiles; t += unit_stride) {
+                t_cur = t;
                 const int split = t / tiles_mn;
                 const int rem = t - split * tiles_mn;
                 const int m0 = ((rem % m_groups) * CLUSTER + cta_rank) * BLOCK_M;
@@ -335,7 +391,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int kb0 = split * g.kb_per_split;
                 const int kb1 = min(g.num_kb, kb0 + g.kb_per_split);
                 for (int kb = kb0; kb < kb1; ++kb) {
-                    mbar_wait(&empty[s], ph ^ 1);
+                    while (!mbar_try_wait(&empty[s], ph ^ 1)) r_pump(false);
                     if (g.dbg_mode == 2) mbar_arrive(&full[s]);
                     else mbar_arrive_expect_tx(&full[s], Cfg::STAGE_BYTES);
                     uint8_t* a_dst = sA + s * Cfg::A_BYTES;
@@ -377,17 +433,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         }
                     }
                     if (++s == STAGES) { s = 0; ph ^= 1; }
-                    if (Cfg::HAS_R && kb == kb0) {
-                        // side-input tile (residual / pre-activation) for this tile's epilogue
-                        mbar_wait(rempty, rph ^ 1);
-                        mbar_arrive_expect_tx(rfull, Cfg::R_BYTES);
-#pragma unroll
-                        for (int i = 0; i < BLOCK_N / 64; ++i)
-                            tma_load_2d(sR + i * (BLOCK_M * 128), &tmR, rfull, n0 + 64 * i, m0);
-                        rph ^= 1;
-                    }
+                    r_pump(false);
                 }
             }
+            r_pump(true);  // whatever side input is still outstanding (nothing else left to load)
             DBG_STAMP(2);
         }
     } else if (warp == 1) {
@@ -447,41 +496,64 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (lane == 0) DBG_STAMP(4);
     } else if (warp >= 4) {
         // ================= epilogue: TMEM -> regs -> fused math -> swizzled smem -> TMA store =========
+        // TMEM is read in 32-column halves that ping-pong between two register sets, so the next
+        // tcgen05.ld is always in flight while the previous half goes through the epilogue math.
         const int ew = warp - 4;
         const int q = warp & 3;    // TMEM lane quadrant this warp may access
         const int half = ew >> 2;  // the two warps of a quadrant alternate over column groups
         uint8_t* stg = sStg + ew * Cfg::STG_PER_WARP;
-        float* bias_s = sBias + ew * BLOCK_N;
         const uint64_t seed = (EPI == B200U_EPI_BIAS_DROP_RES) ? load_seed(g.drop) : 0ull;
         const int rr = q * 32 + lane;  // row inside the tile
         const int sw = lane & 7;       // 128B-swizzle phase of this row
         int as = 0;
-        uint32_t aph = 0, rph = 0;
+        uint32_t aph = 0;
+        uint32_t rpar = 0;  // bit g: parity of the next fill of side-input group g
+        // bias slice of the NEXT tile, fetched into registers by epilogue warp 0 while the current
+        // tile is being processed, published through one smem slot per accumulator stage
+        float bpre[BLOCK_N / 32];
+        auto bias_fetch = [&](int tile) {
+            const int bn0 = ((tile % tiles_mn) / m_groups) * BLOCK_N;
+#pragma unroll
+            for (int i = 0; i < BLOCK_N / 32; ++i) {
+                const int c = bn0 + lane + 32 * i;
+                bpre[i] = (g.bias && c < g.N) ? g.bias[c] : 0.f;
+            }
+        };
+        if (Cfg::HAS_BIAS && ew == 0 && unit0 < total_tiles) bias_fetch(unit0);
         for (int t = unit0; t < total_tiles; t += unit_stride) {
             const int split = t / tiles_mn;
             const int rem = t - split * tiles_mn;
             const int m0 = ((rem % m_groups) * CLUSTER + cta_rank) * BLOCK_M;
             const int n0 = (rem / m_groups) * BLOCK_N;
+            const float* bias_s = sBias + as * BLOCK_N;
             if (Cfg::HAS_BIAS) {
-                // bias slice of this tile -> per-warp smem while the main loop is still running
-                for (int c = lane; c < BLOCK_N; c += 32)
-                    bias_s[c] = (g.bias && n0 + c < g.N) ? g.bias[n0 + c] : 0.f;
-                __syncwarp();
+                if (ew == 0) {
+#pragma unroll
+                    for (int i = 0; i < BLOCK_N / 32; ++i) sBias[as * BLOCK_N + lane + 32 * i] = bpre[i];
+                }
+                // slot `as` was last read two tiles ago; every warp passed the previous tile's barrier since
+                asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+                if (ew == 0 && t + unit_stride < total_tiles) bias_fetch(t + unit_stride);
             }
             mbar_wait(&tfull[as], aph);
             tc_fence_after();
             if (threadIdx.x == 128 && t == unit0) DBG_STAMP(5);
-            if (Cfg::HAS_R) mbar_wait(rfull, rph);
             const int row = m0 + rr;
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BLOCK_N;
-#pragma unroll 1
-            for (int gi = half; gi < Cfg::NUM_GROUPS; gi += 2) {
-                const int col0 = gi * Cfg::GROUP_COLS;
-                if (n0 + col0 >= g.N) break;  // whole group outside the matrix (uniform)
-                if (Cfg::F32_OUT) {
-                    uint32_t r[32];
-                    tmem_ld_32x32(taddr + col0, r);
-                    tmem_ld_wait();
+            bool released = false;  // this warp's arrival on tempty[as]
+            auto release_acc = [&]() {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[as]);
+                released = true;
+            };
+            int gi = half;
+            bool have = gi < NG && n0 + gi * Cfg::GROUP_COLS < g.N;
+            uint32_t ra[32], rb[32];
+            if (have) tmem_ld_32x32(taddr + gi * Cfg::GROUP_COLS, ra);
+            if (Cfg::F32_OUT) {
+                // fp32 output (wgrad reduce-add / fp32 store): 32-column groups, one 4 KB staging tile
+                auto stage_out = [&](const uint32_t (&r)[32], int col0) {
                     if (lane == 0) bulk_wait_read_all();  // staging buffer free again?
                     __syncwarp();
 #pragma unroll
@@ -490,8 +562,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         o.x = __uint_as_float(r[4 * j + 0]); o.y = __uint_as_float(r[4 * j + 1]);
                         o.z = __uint_as_float(r[4 * j + 2]); o.w = __uint_as_float(r[4 * j + 3]);
                         if (EPI == B200U_EPI_STORE_F32) {
-                            o.x += bias_s[col0 + 4 * j + 0]; o.y += bias_s[col0 + 4 * j + 1];
-                            o.z += bias_s[col0 + 4 * j + 2]; o.w += bias_s[col0 + 4 * j + 3];
+                            const float4 bb = *reinterpret_cast<const float4*>(bias_s + col0 + 4 * j);
+                            o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
                         }
                         *reinterpret_cast<float4*>(stg + lane * 128 + ((j ^ sw) << 4)) = o;
                     }
@@ -502,36 +574,67 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         else tma_store_2d(&tmC, stg, n0 + col0, m0 + q * 32);
                         bulk_commit();
                     }
-                } else {
-                    uint32_t r0[32], r1[32];
-                    tmem_ld_32x32(taddr + col0, r0);
-                    tmem_ld_32x32(taddr + col0 + 32, r1);
-                    tmem_ld_wait();
-                    uint8_t* dst = Cfg::HAS_R ? sR + gi * (BLOCK_M * 128) + q * (32 * 128) : stg;
-                    if (!Cfg::HAS_R) {
-                        if (lane == 0) bulk_wait_read_all();  // staging buffer free again?
-                        __syncwarp();
+                };
+#pragma unroll 1
+                while (have) {
+                    int gn = gi + 2;
+                    bool more = gn < NG && n0 + gn * 32 < g.N;
+                    tmem_ld_wait();  // ra
+                    if (more) tmem_ld_32x32(taddr + gn * 32, rb); else release_acc();
+                    stage_out(ra, gi * 32);
+                    if (!more) break;
+                    gi = gn;
+                    gn = gi + 2;
+                    more = gn < NG && n0 + gn * 32 < g.N;
+                    tmem_ld_wait();  // rb
+                    if (more) tmem_ld_32x32(taddr + gn * 32, ra); else release_acc();
+                    stage_out(rb, gi * 32);
+                    gi = gn;
+                    have = more;
+                }
+            } else {
+                int prev = -1;  // side-input group whose TMA store may still be reading its slot
+#pragma unroll 1
+                while (have) {
+                    const int col0 = gi * 64;
+                    const int gn = gi + 2;
+                    const bool more = gn < NG && n0 + gn * 64 < g.N;
+                    uint8_t* slot = Cfg::HAS_R ? sR + gi * Cfg::R_GROUP_BYTES : stg;
+                    uint8_t* dst = Cfg::HAS_R ? slot + q * (32 * 128) : stg;
+                    tmem_ld_wait();                              // ra = columns col0 .. col0+31
+                    tmem_ld_32x32(taddr + col0 + 32, rb);        // lands during the math on ra
+                    if (lane == 0) {
+                        bulk_wait_read_all();  // previous group's TMA store has finished reading smem
+                        if (Cfg::HAS_R && prev >= 0) mbar_arrive(&rempty[prev]);
                     }
+                    if (Cfg::HAS_R) {
+                        mbar_wait(&rfull[gi], (rpar >> gi) & 1u);
+                        rpar ^= 1u << gi;
+                    }
+                    __syncwarp();
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        float v[8], w[8];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i)
-                            v[i] = __uint_as_float(j < 4 ? r0[8 * j + i] : r1[8 * (j - 4) + i]);
+                    for (int j = 0; j < 4; ++j) {
                         uint4 rraw = make_uint4(0, 0, 0, 0);
                         if (Cfg::HAS_R)
-                            rraw = *reinterpret_cast<const uint4*>(sR + gi * (BLOCK_M * 128) + rr * 128 + ((j ^ sw) << 4));
-                        epi_math8<EPI>(v, w, bias_s + col0 + 8 * j, rraw, g, seed, row, n0 + col0 + 8 * j);
-                        uint4 o;
-                        o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]);
-                        o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
+                            rraw = *reinterpret_cast<const uint4*>(slot + rr * 128 + ((j ^ sw) << 4));
+                        uint4 o, o2;
+                        epi_math8<EPI>(&ra[8 * j], bias_s + col0 + 8 * j, rraw, g, seed, row, n0 + col0 + 8 * j, o, o2);
                         *reinterpret_cast<uint4*>(dst + lane * 128 + ((j ^ sw) << 4)) = o;
-                        if (Cfg::DUAL) {
-                            uint4 o2;
-                            o2.x = pack_bf16(w[0], w[1]); o2.y = pack_bf16(w[2], w[3]);
-                            o2.z = pack_bf16(w[4], w[5]); o2.w = pack_bf16(w[6], w[7]);
+                        if (Cfg::DUAL)
                             *reinterpret_cast<uint4*>(stg + 4096 + lane * 128 + ((j ^ sw) << 4)) = o2;
-                        }
+                    }
+                    tmem_ld_wait();                              // rb = columns col0+32 .. col0+63
+                    if (more) tmem_ld_32x32(taddr + gn * 64, ra); else release_acc();
+#pragma unroll
+                    for (int j = 4; j < 8; ++j) {
+                        uint4 rraw = make_uint4(0, 0, 0, 0);
+                        if (Cfg::HAS_R)
+                            rraw = *reinterpret_cast<const uint4*>(slot + rr * 128 + ((j ^ sw) << 4));
+                        uint4 o, o2;
+                        epi_math8<EPI>(&rb[8 * (j - 4)], bias_s + col0 + 8 * j, rraw, g, seed, row, n0 + col0 + 8 * j, o, o2);
+                        *reinterpret_cast<uint4*>(dst + lane * 128 + ((j ^ sw) << 4)) = o;
+                        if (Cfg::DUAL)
+                            *reinterpret_cast<uint4*>(stg + 4096 + lane * 128 + ((j ^ sw) << 4)) = o2;
                     }
                     fence_proxy_async();
                     __syncwarp();
@@ -540,22 +643,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         if (Cfg::DUAL) tma_store_2d(&tmC2, stg + 4096, n0 + col0, m0 + q * 32);
                         bulk_commit();
                     }
+                    prev = gi;
+                    gi = gn;
+                    have = more;
+                }
+                if (Cfg::HAS_R && prev >= 0 && lane == 0) {
+                    bulk_wait_read_all();  // the last store has finished reading its side-input slot
+                    mbar_arrive(&rempty[prev]);
                 }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(&tempty[as]);
-                if (Cfg::HAS_R) {
-                    bulk_wait_read_all();  // the TMA stores have finished reading the side-input tile
-                    mbar_arrive(rempty);
-                }
-            }
-            rph ^= 1;
+            if (!released) release_acc();  // warps that had no column group in this tile
             as ^= 1;
             if (as == 0) aph ^= 1;
         }
-        if (lane == 0) bulk_wait_all();  // all TMA stores of this warp have landed
+        // the TMA stores only have to be done READING shared memory before the CTA exits; their
+        // global writes are complete (and visible to dependent grids) when the grid completes
+        if (lane == 0) bulk_wait_read_all();
         if (threadIdx.x == 128) DBG_STAMP(6);
     }
 
@@ -576,6 +679,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 template <int EPI>
 __global__ void gemm_simt_kernel(const bf16* __restrict__ A, int lda, int a_mn,
                                  const bf16* __restrict__ B, int ldb, int b_mn, const GemmArgs g) {
+    pdl_sync();
     const int row = blockIdx.y * 128 + threadIdx.x;
     const int col0 = blockIdx.x * 32;
     float acc[32];
@@ -682,13 +786,22 @@ static int launch_tc(const b200u_gemm_t* d, GemmArgs& g, cudaStream_t stream) {
     cfg.blockDim = dim3(GEMM_THREADS);
     cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CLUSTER;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (CLUSTER > 1) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = CLUSTER;
+        attr[na].val.clusterDim.y = 1;
+        attr[na].val.clusterDim.z = 1;
+        ++na;
+    }
+    if (pdl_enabled()) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = na;
     B200U_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, tmC2, tmR, g));
     if (prof) prof_end(stream, slot);
     B200U_CHECK_LAUNCH("gemm_tc_kernel");
@@ -708,7 +821,7 @@ static int dispatch_bn(const b200u_gemm_t* d, GemmArgs& g, int block_n, cudaStre
     if (d->impl == 1) {
         dim3 grid((d->N + 31) / 32, (d->M + 127) / 128);
         g.splits = 1;
-        gemm_simt_kernel<EPI><<<grid, 128, 0, stream>>>((const bf16*)d->A, d->lda, d->a_mn_major,
+        launch_k(gemm_simt_kernel<EPI>, dim3(grid), dim3(128), 0, stream, (const bf16*)d->A, d->lda, d->a_mn_major,
                                                         (const bf16*)d->B, d->ldb, d->b_mn_major, g);
         B200U_CHECK_LAUNCH("gemm_simt_kernel");
         return B200U_OK;
@@ -777,20 +890,25 @@ extern "C" int b200u_gemm(const b200u_gemm_t* d, b200u_stream_t stream_) {
     B200U_CHECK_ARG(g.drop.thresh16 == 0 || g.drop.seed_ptr, "b200u_gemm: dropout needs seed_ptr");
     g.num_kb = (d->K + BLOCK_K - 1) / BLOCK_K;
 
-    // tile shape: wide tiles when they still fill the machine, else 128.
+    // tile shape: wide tiles when they still fill the machine, else 128. The fp32 reduce-add
+    // (wgrad) family always prefers 256-wide tiles (MN-major x MN-major 128-wide tiles are shared
+    // memory bandwidth bound) and as many K-splits as still fit ONE wave of CTAs -- measured on
+    // B200 at the C2 shapes (tools/gemm_sweep.py): 768x3072x2624 bn256/s2 14.3 us vs bn128/s1 17.4.
     int block_n = d->block_n;
     const int m_tiles = (d->M + BLOCK_M - 1) / BLOCK_M;
+    const bool reduce = d->epilogue == B200U_EPI_ATOMIC_F32;
     if (block_n == 0) {
         const int t256 = m_tiles * ((d->N + 255) / 256);
-        block_n = (d->N >= 256 && t256 >= num_sms()) ? 256 : 128;
+        if (reduce) block_n = d->N >= 256 ? 256 : 128;
+        else block_n = (d->N >= 256 && t256 >= num_sms()) ? 256 : 128;
     }
     // (epilogues with a side-input tile keep it in smem and write their output over it in place:
     //  3 pipeline stages remain at 256-wide tiles, 5 at 128)
     int splits = d->splits;
-    if (d->epilogue != B200U_EPI_ATOMIC_F32) splits = 1;
+    if (!reduce) splits = 1;
     else if (splits <= 0) {
         const int tiles = m_tiles * ((d->N + block_n - 1) / block_n);
-        splits = (num_sms() + tiles - 1) / tiles;
+        splits = num_sms() / tiles;
         if (splits > g.num_kb) splits = g.num_kb;
         if (splits < 1) splits = 1;
     }

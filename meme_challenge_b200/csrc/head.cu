@@ -14,6 +14,7 @@ namespace b200u {
 __global__ void __launch_bounds__(256)
 pooler_fwd_kernel(const bf16* __restrict__ h, size_t row_stride, const float* __restrict__ W,
                   const float* __restrict__ bias, float* __restrict__ pooled, int H) {
+    pdl_sync();
     extern __shared__ float sx[];  // [H]
     const int b = blockIdx.y;
     for (int k = threadIdx.x; k < H; k += blockDim.x) sx[k] = __bfloat162float(h[(size_t)b * row_stride + k]);
@@ -41,6 +42,7 @@ pooler_bwd_kernel(const float* __restrict__ dpooled, const float* __restrict__ p
                   const bf16* __restrict__ h, size_t row_stride, const float* __restrict__ W,
                   float* __restrict__ dW, float* __restrict__ db, bf16* __restrict__ dh,
                   size_t dh_row_stride, int B, int H) {
+    pdl_sync();
     extern __shared__ float sm[];
     const int nwb = (H + 7) / 8;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -87,6 +89,7 @@ pooler_bwd_kernel(const float* __restrict__ dpooled, const float* __restrict__ p
 __global__ void __launch_bounds__(256)
 linear_small_fwd_kernel(const float* __restrict__ x, const float* __restrict__ W,
                         const float* __restrict__ bias, float* __restrict__ out, int B, int C, int K) {
+    pdl_sync();
     const int lane = threadIdx.x & 31;
     const int idx = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (idx >= B * C) return;
@@ -103,6 +106,7 @@ __global__ void __launch_bounds__(256)
 linear_small_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ x,
                         const float* __restrict__ W, float* __restrict__ dx, float* __restrict__ dW,
                         float* __restrict__ db, int B, int C, int K) {
+    pdl_sync();
     if ((int)blockIdx.x < B) {
         const int b = blockIdx.x;
         if (!dx) return;
@@ -132,6 +136,7 @@ __global__ void __launch_bounds__(256)
 bce_logits_kernel(const float* __restrict__ logits, const float* __restrict__ labels,
                   float pos_weight, float grad_scale, float* __restrict__ loss, float* __restrict__ dlogits,
                   float* __restrict__ probs, int B) {
+    pdl_sync();
     __shared__ float red[8];
     float part = 0.f;
     for (int b = threadIdx.x; b < B; b += blockDim.x) {
@@ -162,7 +167,7 @@ extern "C" int b200u_pooler_fwd(const void* h, long long row_stride, const float
     cudaStream_t stream = (cudaStream_t)stream_;
     B200U_CHECK_ARG(h && W && bias && pooled && H % 4 == 0, "pooler_fwd: bad arguments");
     if (B == 0) return B200U_OK;
-    pooler_fwd_kernel<<<dim3((H + 63) / 64, B), 256, H * sizeof(float), stream>>>((const bf16*)h, (size_t)row_stride, W, bias, pooled, H);
+    launch_k(pooler_fwd_kernel, dim3(dim3((H + 63) / 64, B)), dim3(256), H * sizeof(float), stream, (const bf16*)h, (size_t)row_stride, W, bias, pooled, H);
     B200U_CHECK_LAUNCH("pooler_fwd");
     return B200U_OK;
 }
@@ -173,7 +178,7 @@ extern "C" int b200u_pooler_bwd(const float* dpooled, const float* pooled, const
     cudaStream_t stream = (cudaStream_t)stream_;
     B200U_CHECK_ARG(dpooled && pooled && h && W && dW && dh && H % 4 == 0 && row_stride % 4 == 0, "pooler_bwd: bad arguments");
     if (B == 0) return B200U_OK;
-    pooler_bwd_kernel<<<(H + 7) / 8 + B, 256, H * sizeof(float), stream>>>(dpooled, pooled, (const bf16*)h, (size_t)row_stride, W, dW, db, (bf16*)dh, (size_t)dh_row_stride, B, H);
+    launch_k(pooler_bwd_kernel, dim3((H + 7) / 8 + B), dim3(256), H * sizeof(float), stream, dpooled, pooled, (const bf16*)h, (size_t)row_stride, W, dW, db, (bf16*)dh, (size_t)dh_row_stride, B, H);
     B200U_CHECK_LAUNCH("pooler_bwd");
     return B200U_OK;
 }
@@ -183,7 +188,7 @@ extern "C" int b200u_linear_small_fwd(const float* x, const float* W, const floa
     cudaStream_t stream = (cudaStream_t)stream_;
     B200U_CHECK_ARG(x && W && out, "linear_small_fwd: null pointer");
     if (B * C == 0) return B200U_OK;
-    linear_small_fwd_kernel<<<(B * C + 7) / 8, 256, 0, stream>>>(x, W, bias, out, B, C, K);
+    launch_k(linear_small_fwd_kernel, dim3((B * C + 7) / 8), dim3(256), 0, stream, x, W, bias, out, B, C, K);
     B200U_CHECK_LAUNCH("linear_small_fwd");
     return B200U_OK;
 }
@@ -193,7 +198,7 @@ extern "C" int b200u_linear_small_bwd(const float* dout, const float* x, const f
     cudaStream_t stream = (cudaStream_t)stream_;
     B200U_CHECK_ARG(dout && x && W && dW, "linear_small_bwd: null pointer");
     if (B * C == 0) return B200U_OK;
-    linear_small_bwd_kernel<<<B + C, 256, 0, stream>>>(dout, x, W, dx, dW, db, B, C, K);
+    launch_k(linear_small_bwd_kernel, dim3(B + C), dim3(256), 0, stream, dout, x, W, dx, dW, db, B, C, K);
     B200U_CHECK_LAUNCH("linear_small_bwd");
     return B200U_OK;
 }
@@ -203,7 +208,7 @@ extern "C" int b200u_bce_logits(const float* logits, const float* labels, float 
                                 b200u_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     B200U_CHECK_ARG(logits && labels && B > 0, "bce_logits: bad arguments");
-    bce_logits_kernel<<<1, 256, 0, stream>>>(logits, labels, pos_weight, grad_scale, loss, dlogits, probs, B);
+    launch_k(bce_logits_kernel, dim3(1), dim3(256), 0, stream, logits, labels, pos_weight, grad_scale, loss, dlogits, probs, B);
     B200U_CHECK_LAUNCH("bce_logits");
     return B200U_OK;
 }

@@ -14,6 +14,7 @@ namespace b200u {
 // sumsq += sum g[i]^2  (double accumulation across blocks)
 __global__ void __launch_bounds__(256)
 sumsq_kernel(const float* __restrict__ g, size_t n, double* __restrict__ sumsq) {
+    pdl_sync();
     float acc = 0.f;
     const size_t nvec = n >> 2;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
@@ -37,6 +38,7 @@ sumsq_kernel(const float* __restrict__ g, size_t n, double* __restrict__ sumsq) 
 // (clip_grad_norm_ semantics applied to the already-averaged gradients)
 __global__ void clip_coef_kernel(const double* __restrict__ sumsq, float pre_scale, float max_norm,
                                  float* __restrict__ coef, float* __restrict__ norm_out) {
+    pdl_sync();
     const float norm = pre_scale * (float)sqrt(*sumsq);
     float c = 1.0f;
     if (max_norm > 0.f) {
@@ -60,6 +62,7 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
             const int* __restrict__ chunk_run, int num_runs, const float* __restrict__ coef_ptr,
             const float* __restrict__ lr_ptr, const unsigned long long* __restrict__ step_ptr,
             float beta1, float beta2, float eps, int zero_grad, float* __restrict__ g_mut) {
+    pdl_sync();
     const float coef = coef_ptr ? *coef_ptr : 1.0f;
     const float lr = *lr_ptr;
     // step index lives on the device so a captured CUDA graph advances it on every replay
@@ -113,7 +116,8 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
     }
 }
 
-__global__ void counter_add_kernel(unsigned long long* c, unsigned long long inc) { *c += inc; }
+__global__ void counter_add_kernel(unsigned long long* c, unsigned long long inc) {
+    pdl_sync(); *c += inc; }
 
 }  // namespace b200u
 
@@ -124,7 +128,7 @@ extern "C" int b200u_counter_add(unsigned long long* counter, unsigned long long
                                  b200u_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     B200U_CHECK_ARG(counter, "counter_add: null pointer");
-    counter_add_kernel<<<1, 1, 0, stream>>>(counter, inc);
+    launch_k(counter_add_kernel, dim3(1), dim3(1), 0, stream, counter, inc);
     B200U_CHECK_LAUNCH("counter_add");
     return B200U_OK;
 }
@@ -137,7 +141,7 @@ extern "C" int b200u_grad_sumsq(const float* g, size_t n, double* sumsq, b200u_s
     const size_t cap = (size_t)num_sms() * 8;
     if (grid > cap) grid = cap;
     if (grid < 1) grid = 1;
-    sumsq_kernel<<<(int)grid, 256, 0, stream>>>(g, n, sumsq);
+    launch_k(sumsq_kernel, dim3((int)grid), dim3(256), 0, stream, g, n, sumsq);
     B200U_CHECK_LAUNCH("grad_sumsq");
     return B200U_OK;
 }
@@ -146,7 +150,7 @@ extern "C" int b200u_clip_coef(const double* sumsq, float pre_scale, float max_n
                                float* norm_out, b200u_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     B200U_CHECK_ARG(sumsq && coef, "clip_coef: null pointer");
-    clip_coef_kernel<<<1, 1, 0, stream>>>(sumsq, pre_scale, max_norm, coef, norm_out);
+    launch_k(clip_coef_kernel, dim3(1), dim3(1), 0, stream, sumsq, pre_scale, max_norm, coef, norm_out);
     B200U_CHECK_LAUNCH("clip_coef");
     return B200U_OK;
 }
@@ -164,7 +168,7 @@ extern "C" int b200u_adam_step(float* p, float* g, float* m, float* v, void* sha
     size_t grid = nchunks;
     const size_t cap = (size_t)num_sms() * 16;
     if (grid > cap) grid = cap;
-    adam_kernel<<<(int)grid, 256, 0, stream>>>(p, g, m, v, (bf16*)shadow_bf16, n, run_start, run_wd, chunk_run, num_runs, coef, lr, step, beta1, beta2, eps, zero_grad, g);
+    launch_k(adam_kernel, dim3((int)grid), dim3(256), 0, stream, p, g, m, v, (bf16*)shadow_bf16, n, run_start, run_wd, chunk_run, num_runs, coef, lr, step, beta1, beta2, eps, zero_grad, g);
     B200U_CHECK_LAUNCH("adam_step");
     return B200U_OK;
 }

@@ -17,6 +17,7 @@ namespace b200u {
 // inv[r] = 1 / max(||v_r||, eps)   (F.normalize semantics), one warp per row.
 __global__ void __launch_bounds__(256)
 row_inv_norm_kernel(const float* __restrict__ v, float* __restrict__ inv, int rows, int D, float eps) {
+    pdl_sync();
     const int lane = threadIdx.x & 31;
     const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (r >= rows) return;
@@ -35,6 +36,7 @@ cosine_cost_kernel(const float* __restrict__ x, const float* __restrict__ y,
                    const float* __restrict__ xinv, const float* __restrict__ yinv,
                    const unsigned char* __restrict__ x_pad, const unsigned char* __restrict__ y_pad,
                    float* __restrict__ cost, int M, int N, int D) {
+    pdl_sync();
     const int lane = threadIdx.x & 31;
     const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int m = blockIdx.y, b = blockIdx.z;
@@ -55,6 +57,7 @@ __global__ void __launch_bounds__(256)
 ipot_kernel(const float* __restrict__ C, const unsigned char* __restrict__ x_pad,
             const unsigned char* __restrict__ y_pad, float* __restrict__ T_out, int M, int N, int Mp,
             float beta, int iterations, int k_inner) {
+    pdl_sync();
     extern __shared__ float sm[];
     float* A = sm;
     float* T = A + (size_t)N * Mp;
@@ -132,6 +135,7 @@ ipot_kernel(const float* __restrict__ C, const unsigned char* __restrict__ x_pad
 __global__ void __launch_bounds__(256)
 ot_distance_kernel(const float* __restrict__ C, const float* __restrict__ T, float* __restrict__ dist,
                    int M, int N) {
+    pdl_sync();
     __shared__ float red[8];
     const int b = blockIdx.x;
     float s = 0.f;
@@ -158,6 +162,7 @@ cosine_cost_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y,
                        const unsigned char* __restrict__ x_pad, const unsigned char* __restrict__ y_pad,
                        const float* __restrict__ T, const float* __restrict__ ddist,
                        float* __restrict__ dx, float* __restrict__ dy, int M, int N, int D) {
+    pdl_sync();
     extern __shared__ float sm[];  // coefficients of the other side's rows
     __shared__ float red[8];
     const int b = blockIdx.z, which = blockIdx.y, r = blockIdx.x;
@@ -205,11 +210,11 @@ extern "C" int b200u_cosine_cost(const float* x, const float* y, const unsigned 
     cudaStream_t stream = (cudaStream_t)stream_;
     B200U_CHECK_ARG(x && y && cost && xinv && yinv && M > 0 && N > 0 && D > 0, "cosine_cost: bad arguments");
     if (B == 0) return B200U_OK;
-    row_inv_norm_kernel<<<(B * M + 7) / 8, 256, 0, stream>>>(x, xinv, B * M, D, eps);
+    launch_k(row_inv_norm_kernel, dim3((B * M + 7) / 8), dim3(256), 0, stream, x, xinv, B * M, D, eps);
     B200U_CHECK_LAUNCH("row_inv_norm(x)");
-    row_inv_norm_kernel<<<(B * N + 7) / 8, 256, 0, stream>>>(y, yinv, B * N, D, eps);
+    launch_k(row_inv_norm_kernel, dim3((B * N + 7) / 8), dim3(256), 0, stream, y, yinv, B * N, D, eps);
     B200U_CHECK_LAUNCH("row_inv_norm(y)");
-    cosine_cost_kernel<<<dim3((N + 7) / 8, M, B), 256, 0, stream>>>(x, y, xinv, yinv, x_pad, y_pad, cost, M, N, D);
+    launch_k(cosine_cost_kernel, dim3(dim3((N + 7) / 8, M, B)), dim3(256), 0, stream, x, y, xinv, yinv, x_pad, y_pad, cost, M, N, D);
     B200U_CHECK_LAUNCH("cosine_cost");
     return B200U_OK;
 }
@@ -228,7 +233,7 @@ extern "C" int b200u_ipot(const float* cost, const unsigned char* x_pad, const u
         B200U_CHECK_CUDA(cudaFuncSetAttribute(ipot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         set_for = smem;
     }
-    ipot_kernel<<<B, 256, smem, stream>>>(cost, x_pad, y_pad, T, M, N, Mp, beta, iterations, k);
+    launch_k(ipot_kernel, dim3(B), dim3(256), smem, stream, cost, x_pad, y_pad, T, M, N, Mp, beta, iterations, k);
     B200U_CHECK_LAUNCH("ipot");
     return B200U_OK;
 }
@@ -238,7 +243,7 @@ extern "C" int b200u_ot_distance(const float* cost, const float* T, float* dist,
     cudaStream_t stream = (cudaStream_t)stream_;
     B200U_CHECK_ARG(cost && T && dist, "ot_distance: null pointer");
     if (B == 0) return B200U_OK;
-    ot_distance_kernel<<<B, 256, 0, stream>>>(cost, T, dist, M, N);
+    launch_k(ot_distance_kernel, dim3(B), dim3(256), 0, stream, cost, T, dist, M, N);
     B200U_CHECK_LAUNCH("ot_distance");
     return B200U_OK;
 }
@@ -251,7 +256,7 @@ extern "C" int b200u_cosine_cost_bwd(const float* x, const float* y, const float
     B200U_CHECK_ARG(x && y && xinv && yinv && T && ddist && dx && dy, "cosine_cost_bwd: null pointer");
     if (B == 0) return B200U_OK;
     const int mx = M > N ? M : N;
-    cosine_cost_bwd_kernel<<<dim3(mx, 2, B), 256, mx * sizeof(float), stream>>>(x, y, xinv, yinv, x_pad, y_pad, T, ddist, dx, dy, M, N, D);
+    launch_k(cosine_cost_bwd_kernel, dim3(dim3(mx, 2, B)), dim3(256), mx * sizeof(float), stream, x, y, xinv, yinv, x_pad, y_pad, T, ddist, dx, dy, M, N, D);
     B200U_CHECK_LAUNCH("cosine_cost_bwd");
     return B200U_OK;
 }

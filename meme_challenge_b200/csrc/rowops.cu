@@ -76,6 +76,7 @@ __global__ void __launch_bounds__(256)
 layernorm_fwd_kernel(const TIn* __restrict__ x, const float* __restrict__ gamma,
                      const float* __restrict__ beta, TOut* __restrict__ y, float* __restrict__ mean_out,
                      float* __restrict__ rstd_out, int M, int H, float eps, DropoutCfg drop) {
+    pdl_sync();
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= M) return;
@@ -129,6 +130,7 @@ layernorm_bwd_kernel(const bf16* __restrict__ dy, const TX* __restrict__ x,
                      const float* __restrict__ gamma, bf16* __restrict__ dx, bf16* __restrict__ dz,
                      float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias,
                      int M, int H, DropoutCfg drop, int drop_on_input) {
+    pdl_sync();
     extern __shared__ float red[];  // [warps][H]
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -234,6 +236,7 @@ layernorm_bwd_kernel(const bf16* __restrict__ dy, const TX* __restrict__ x,
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 colsum_kernel(const bf16* __restrict__ x, int ldx, float* __restrict__ out, int M, int N) {
+    pdl_sync();
     __shared__ float red[8][256];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int col = blockIdx.x * 256 + lane * 8;
@@ -262,6 +265,7 @@ colsum_kernel(const bf16* __restrict__ x, int ldx, float* __restrict__ out, int 
 
 // fp32 -> bf16 cast (n multiple of 8), grid-stride.
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ y, size_t nvec) {
+    pdl_sync();
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nvec;
          i += (size_t)gridDim.x * blockDim.x) {
         float f[8];
@@ -273,6 +277,7 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ x, bf16* __restri
 // out = dy * gelu_erf'(u)  (backward of the standalone dense+GELU transforms of the heads)
 __global__ void dgelu_mul_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ u,
                                  bf16* __restrict__ out, size_t nvec) {
+    pdl_sync();
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nvec;
          i += (size_t)gridDim.x * blockDim.x) {
         float a[8], b[8];
@@ -293,6 +298,7 @@ __global__ void __launch_bounds__(256)
 gather_rows_kernel(const bf16* __restrict__ txt, const bf16* __restrict__ img,
                    const long long* __restrict__ gidx, bf16* __restrict__ out, int B, int T, int R,
                    int L, int H) {
+    pdl_sync();
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= B * L) return;
@@ -311,6 +317,7 @@ __global__ void __launch_bounds__(256)
 gather_rows_bwd_kernel(const bf16* __restrict__ dout, const long long* __restrict__ gidx,
                        bf16* __restrict__ dtxt, bf16* __restrict__ dimg, int B, int T, int R, int L,
                        int H) {
+    pdl_sync();
     const int lane = threadIdx.x & 31;
     const int srow = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int S = T + R;
@@ -377,11 +384,11 @@ extern "C" int b200u_layernorm_fwd(const void* x, int x_dtype, const float* gamm
     B200U_CHECK_ARG(dc.thresh16 == 0 || dc.seed_ptr, "layernorm_fwd: dropout needs seed_ptr");
     const int grid = (M + 7) / 8;
     if (x_dtype == B200U_BF16 && y_dtype == B200U_BF16)
-        layernorm_fwd_kernel<bf16, bf16><<<grid, 256, 0, stream>>>((const bf16*)x, gamma, beta, (bf16*)y, mean, rstd, M, H, eps, dc);
+        launch_k(layernorm_fwd_kernel<bf16, bf16>, dim3(grid), dim3(256), 0, stream, (const bf16*)x, gamma, beta, (bf16*)y, mean, rstd, M, H, eps, dc);
     else if (x_dtype == B200U_F32 && y_dtype == B200U_BF16)
-        layernorm_fwd_kernel<float, bf16><<<grid, 256, 0, stream>>>((const float*)x, gamma, beta, (bf16*)y, mean, rstd, M, H, eps, dc);
+        launch_k(layernorm_fwd_kernel<float, bf16>, dim3(grid), dim3(256), 0, stream, (const float*)x, gamma, beta, (bf16*)y, mean, rstd, M, H, eps, dc);
     else if (x_dtype == B200U_F32 && y_dtype == B200U_F32)
-        layernorm_fwd_kernel<float, float><<<grid, 256, 0, stream>>>((const float*)x, gamma, beta, (float*)y, mean, rstd, M, H, eps, dc);
+        launch_k(layernorm_fwd_kernel<float, float>, dim3(grid), dim3(256), 0, stream, (const float*)x, gamma, beta, (float*)y, mean, rstd, M, H, eps, dc);
     else
         B200U_CHECK_ARG(false, "layernorm_fwd: unsupported dtype combination %d -> %d", x_dtype, y_dtype);
     B200U_CHECK_LAUNCH("layernorm_fwd");
@@ -404,9 +411,9 @@ extern "C" int b200u_layernorm_bwd(const void* dy, const void* x, int x_dtype, c
     if (grid > num_sms()) grid = num_sms();
     const size_t smem = (size_t)8 * H * sizeof(float);
     if (x_dtype == B200U_BF16)
-        layernorm_bwd_kernel<bf16><<<grid, 256, smem, stream>>>((const bf16*)dy, (const bf16*)x, mean, rstd, gamma, (bf16*)dx, (bf16*)dz, dgamma, dbeta, dbias, M, H, dc, drop_on_input);
+        launch_k(layernorm_bwd_kernel<bf16>, dim3(grid), dim3(256), smem, stream, (const bf16*)dy, (const bf16*)x, mean, rstd, gamma, (bf16*)dx, (bf16*)dz, dgamma, dbeta, dbias, M, H, dc, drop_on_input);
     else if (x_dtype == B200U_F32)
-        layernorm_bwd_kernel<float><<<grid, 256, smem, stream>>>((const bf16*)dy, (const float*)x, mean, rstd, gamma, (bf16*)dx, (bf16*)dz, dgamma, dbeta, dbias, M, H, dc, drop_on_input);
+        launch_k(layernorm_bwd_kernel<float>, dim3(grid), dim3(256), smem, stream, (const bf16*)dy, (const float*)x, mean, rstd, gamma, (bf16*)dx, (bf16*)dz, dgamma, dbeta, dbias, M, H, dc, drop_on_input);
     else
         B200U_CHECK_ARG(false, "layernorm_bwd: unsupported x dtype %d", x_dtype);
     B200U_CHECK_LAUNCH("layernorm_bwd");
@@ -422,7 +429,7 @@ extern "C" int b200u_colsum_accum(const void* x, int ldx, float* out, int M, int
     int gy = (2 * num_sms() + gx - 1) / gx;
     if (gy > (M + 7) / 8) gy = (M + 7) / 8;
     if (gy < 1) gy = 1;
-    colsum_kernel<<<dim3(gx, gy), 256, 0, stream>>>((const bf16*)x, ldx, out, M, N);
+    launch_k(colsum_kernel, dim3(dim3(gx, gy)), dim3(256), 0, stream, (const bf16*)x, ldx, out, M, N);
     B200U_CHECK_LAUNCH("colsum_accum");
     return B200U_OK;
 }
@@ -435,7 +442,7 @@ extern "C" int b200u_cast_f32_to_bf16(const float* x, void* y, size_t n, b200u_s
     size_t grid = (nvec + 255) / 256;
     const size_t cap = (size_t)num_sms() * 16;
     if (grid > cap) grid = cap;
-    cast_f32_bf16_kernel<<<(int)grid, 256, 0, stream>>>(x, (bf16*)y, nvec);
+    launch_k(cast_f32_bf16_kernel, dim3((int)grid), dim3(256), 0, stream, x, (bf16*)y, nvec);
     B200U_CHECK_LAUNCH("cast_f32_to_bf16");
     return B200U_OK;
 }
@@ -448,7 +455,7 @@ extern "C" int b200u_dgelu_mul(const void* dy, const void* u, void* out, size_t 
     size_t grid = (nvec + 255) / 256;
     const size_t cap = (size_t)num_sms() * 16;
     if (grid > cap) grid = cap;
-    dgelu_mul_kernel<<<(int)grid, 256, 0, stream>>>((const bf16*)dy, (const bf16*)u, (bf16*)out, nvec);
+    launch_k(dgelu_mul_kernel, dim3((int)grid), dim3(256), 0, stream, (const bf16*)dy, (const bf16*)u, (bf16*)out, nvec);
     B200U_CHECK_LAUNCH("dgelu_mul");
     return B200U_OK;
 }
@@ -458,7 +465,7 @@ extern "C" int b200u_gather_rows(const void* txt, const void* img, const long lo
     cudaStream_t stream = (cudaStream_t)stream_;
     B200U_CHECK_ARG(txt && img && gather_index && out && H % 8 == 0, "gather_rows: bad arguments");
     if (B * L == 0) return B200U_OK;
-    gather_rows_kernel<<<(B * L + 7) / 8, 256, 0, stream>>>((const bf16*)txt, (const bf16*)img, gather_index, (bf16*)out, B, T, R, L, H);
+    launch_k(gather_rows_kernel, dim3((B * L + 7) / 8), dim3(256), 0, stream, (const bf16*)txt, (const bf16*)img, gather_index, (bf16*)out, B, T, R, L, H);
     B200U_CHECK_LAUNCH("gather_rows");
     return B200U_OK;
 }
@@ -470,7 +477,7 @@ extern "C" int b200u_gather_rows_bwd(const void* dout, const long long* gather_i
     CHECK_H(H);
     B200U_CHECK_ARG(dout && gather_index && dtxt && dimg, "gather_rows_bwd: null pointer");
     if (B * (T + R) == 0) return B200U_OK;
-    gather_rows_bwd_kernel<<<(B * (T + R) + 7) / 8, 256, 0, stream>>>((const bf16*)dout, gather_index, (bf16*)dtxt, (bf16*)dimg, B, T, R, L, H);
+    launch_k(gather_rows_bwd_kernel, dim3((B * (T + R) + 7) / 8), dim3(256), 0, stream, (const bf16*)dout, gather_index, (bf16*)dtxt, (bf16*)dimg, B, T, R, L, H);
     B200U_CHECK_LAUNCH("gather_rows_bwd");
     return B200U_OK;
 }

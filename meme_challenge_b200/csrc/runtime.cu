@@ -33,6 +33,10 @@ bool prof_begin(cudaStream_t st, double flops, int* slot) {
 }
 void prof_end(cudaStream_t st, int slot) { cudaEventRecord(g_prof[slot].e1, st); }
 
+static int g_pdl = 1;
+bool pdl_enabled() { return g_pdl != 0; }
+void set_pdl(int on) { g_pdl = on; }
+
 int num_sms() {
     static int cached = 0;
     if (!cached) {
@@ -51,6 +55,11 @@ int num_sms() {
 extern "C" const char* b200u_last_error_string(void) { return b200u::g_err; }
 
 extern "C" int b200u_version(void) { return 100; }
+
+extern "C" int b200u_set_pdl(int on) {
+    b200u::set_pdl(on);
+    return B200U_OK;
+}
 
 extern "C" long long b200u_launch_count(void) { return __atomic_load_n(&b200u::g_launches, __ATOMIC_RELAXED); }
 

@@ -198,7 +198,12 @@ class TrainStep(object):
     # ------------------------------------------------------------------ CUDA-graph replay
     def capture(self, example_batches, warmup=3):
         """Capture one full optimizer step (all micro-batches + optimizer) in a CUDA graph over
-        static input buffers. Returns the static buffers; fill them and call replay()."""
+        static input buffers. Returns the static buffers; fill them and call replay().
+
+        With world_size > 1 the bucket all-reduces are captured too: the collectives issued from the
+        backward hooks fork onto the process group's stream inside the capture and `wait()` joins
+        them before the optimizer nodes, so the replayed graph keeps the comm/backward overlap.
+        (thread_local capture mode: the NCCL watchdog thread may poll events while we capture.)"""
         static = [{k: v.clone() for k, v in b.items() if torch.is_tensor(v)} for b in example_batches]
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
@@ -208,7 +213,8 @@ class TrainStep(object):
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
+        mode = "thread_local" if self.world > 1 else "global"
+        with torch.cuda.graph(graph, capture_error_mode=mode):
             outs = self.step(static)
         self._graph, self._static, self._static_out = graph, static, outs
         return static
