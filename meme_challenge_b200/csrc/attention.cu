@@ -88,13 +88,18 @@ __device__ __forceinline__ void mma_x(float (&o)[8][4], uint32_t a0, uint32_t a1
 // finish with load_tiles_wait() before the __syncthreads() that publishes the tiles.
 __device__ __forceinline__ void load_tile(bf16* dst, const bf16* src, int ld, int valid, int rows,
                                           int tid, int nthreads, int valid_chunks = 8) {
-    for (int i = tid; i < rows * 8; i += nthreads) {
-        const int r = i >> 3, ch = i & 7;
-        bf16* d = dst + sw_off(r, ch);
-        if (r < valid && ch < valid_chunks) {
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(d)),
-                         "l"(src + (size_t)r * ld + ch * 8)
-                         : "memory");
+    // a thread keeps its 16-byte chunk column and walks the rows in steps of nthreads/8 (a multiple
+    // of 8), so the swizzled chunk, both strides and the chunk predicate are loop invariant
+    const int ch = tid & 7;
+    const int rstep = nthreads >> 3;
+    int r = tid >> 3;
+    bf16* d = dst + r * HD + ((ch ^ (r & 7)) << 3);
+    const bf16* s = src + (size_t)r * ld + ch * 8;
+    const size_t sstep = (size_t)rstep * ld;
+    const bool chunk_ok = ch < valid_chunks;
+    for (; r < rows; r += rstep, d += rstep * HD, s += sstep) {
+        if (chunk_ok && r < valid) {
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(d)), "l"(s) : "memory");
         } else {
             *reinterpret_cast<uint4*>(d) = make_uint4(0, 0, 0, 0);
         }
@@ -141,7 +146,9 @@ attn_fwd_kernel(const bf16* __restrict__ qkv, const float* __restrict__ mask, bf
     load_tile(sQ, base + (size_t)q0 * ld, ld, L - q0, TQ, tid, 128);
     load_tile(sK, base + H, ld, L, LP, tid, 128);
     load_tile(sV, base + 2 * H, ld, L, LP, tid, 128);
-    for (int j = tid; j < LP; j += 128) sM[j] = (j < L) ? mask[(size_t)b * L + j] : -INFINITY;
+    // additive mask in the log2 domain, padded with -inf to the 64-key chunks the loop sweeps
+    const int LP64 = (L + 63) & ~63;
+    for (int j = tid; j < LP64; j += 128) sM[j] = (j < L) ? mask[(size_t)b * L + j] * LOG2E : -INFINITY;
     load_tiles_wait();
     __syncthreads();
 
@@ -154,7 +161,9 @@ attn_fwd_kernel(const bf16* __restrict__ qkv, const float* __restrict__ mask, bf
     const int i0 = r0 + g, i1 = r0 + g + 8;
     const uint32_t key = drop.thresh16 ? attn_key(load_seed(drop), drop.stream) : 0u;
     const uint32_t pb0 = attn_pair_base(bh, i0, L), pb1 = attn_pair_base(bh, i1, L);
+    constexpr float SC = 0.125f * LOG2E;  // scores / sqrt(64) (model/layer.py:86), in log2 units
 
+    // running max m and sum l of exp2(score2 - m), score2 = (q.k / 8 + mask) * log2(e)
     float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
     float o[8][4];
 #pragma unroll
@@ -171,10 +180,9 @@ attn_fwd_kernel(const bf16* __restrict__ qkv, const float* __restrict__ mask, bf
         float cm0 = -INFINITY, cm1 = -INFINITY;
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) {
-            const int j = c0 + nt * 8 + t2;
-            const float ma = (j < LP) ? sM[j] : -INFINITY, mb = (j + 1 < LP) ? sM[j + 1] : -INFINITY;
-            s[nt][0] = s[nt][0] * 0.125f + ma; s[nt][1] = s[nt][1] * 0.125f + mb;
-            s[nt][2] = s[nt][2] * 0.125f + ma; s[nt][3] = s[nt][3] * 0.125f + mb;
+            const float2 mk = *reinterpret_cast<const float2*>(sM + c0 + nt * 8 + t2);
+            s[nt][0] = fmaf(s[nt][0], SC, mk.x); s[nt][1] = fmaf(s[nt][1], SC, mk.y);
+            s[nt][2] = fmaf(s[nt][2], SC, mk.x); s[nt][3] = fmaf(s[nt][3], SC, mk.y);
             cm0 = fmaxf(cm0, fmaxf(s[nt][0], s[nt][1]));
             cm1 = fmaxf(cm1, fmaxf(s[nt][2], s[nt][3]));
         }
@@ -183,7 +191,7 @@ attn_fwd_kernel(const bf16* __restrict__ qkv, const float* __restrict__ mask, bf
         cm1 = fmaxf(cm1, __shfl_xor_sync(0xffffffffu, cm1, 1));
         cm1 = fmaxf(cm1, __shfl_xor_sync(0xffffffffu, cm1, 2));
         const float n0 = fmaxf(m0, cm0), n1 = fmaxf(m1, cm1);
-        const float corr0 = exp2f((m0 - n0) * LOG2E), corr1 = exp2f((m1 - n1) * LOG2E);
+        const float corr0 = ex2_approx(m0 - n0), corr1 = ex2_approx(m1 - n1);
         m0 = n0; m1 = n1;
         l0 *= corr0; l1 *= corr1;
 #pragma unroll
@@ -197,8 +205,8 @@ attn_fwd_kernel(const bf16* __restrict__ qkv, const float* __restrict__ mask, bf
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     const int nt = 2 * kt + e;
-                    p[e][0] = exp2f((s[nt][0] - m0) * LOG2E); p[e][1] = exp2f((s[nt][1] - m0) * LOG2E);
-                    p[e][2] = exp2f((s[nt][2] - m1) * LOG2E); p[e][3] = exp2f((s[nt][3] - m1) * LOG2E);
+                    p[e][0] = ex2_approx(s[nt][0] - m0); p[e][1] = ex2_approx(s[nt][1] - m0);
+                    p[e][2] = ex2_approx(s[nt][2] - m1); p[e][3] = ex2_approx(s[nt][3] - m1);
                     l0 += p[e][0] + p[e][1];
                     l1 += p[e][2] + p[e][3];
                     if (drop.thresh16) {  // dropout on the probabilities (model/layer.py:95)
@@ -220,8 +228,9 @@ attn_fwd_kernel(const bf16* __restrict__ qkv, const float* __restrict__ mask, bf
     l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
     l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
     if ((lane & 3) == 0 && lse) {
-        if (i0 < L) lse[(size_t)bh * L + i0] = m0 + logf(l0);
-        if (i1 < L) lse[(size_t)bh * L + i1] = m1 + logf(l1);
+        // natural-log log-sum-exp of the masked, scaled scores
+        if (i0 < L) lse[(size_t)bh * L + i0] = (m0 + log2f(l0)) * 0.69314718055994530942f;
+        if (i1 < L) lse[(size_t)bh * L + i1] = (m1 + log2f(l1)) * 0.69314718055994530942f;
     }
     const float inv0 = (drop.thresh16 ? drop.scale : 1.0f) / l0, inv1 = (drop.thresh16 ? drop.scale : 1.0f) / l1;
     bf16* out = ctx + (size_t)b * L * H + h * HD;
@@ -456,7 +465,7 @@ static DropoutCfg make_drop(const b200u_dropout_t* d) {
 static int launch_fwd(const void* qkv, const float* mask, void* ctx, float* lse, int B, int L, int nh,
                       int H, DropoutCfg dc, cudaStream_t stream) {
     const int LP = (L + 15) / 16 * 16;
-    const size_t smem = (size_t)(2 * LP + TQ) * HD * 2 + (size_t)LP * 4;
+    const size_t smem = (size_t)(2 * LP + TQ) * HD * 2 + (size_t)((L + 63) & ~63) * 4;
     static size_t set_for = 0;
     if (smem > set_for) {
         B200U_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -300,6 +300,19 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tmap, 
         ::"r"(smem_u32(dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
+// Same with the destination and barrier given as shared-space addresses (kept in uniform registers
+// by the warp-uniform producer loop of the GEMM).
+__device__ __forceinline__ void tma_load_2d_u(uint32_t dst, const CUtensorMap* tmap, uint32_t bar,
+                                              int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes "
+        "[%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx_u(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
 // smem (swizzled box) -> global, bulk-group completion; OOB parts of the box are clipped.
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tmap, const void* src, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tmap),
@@ -315,6 +328,9 @@ __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* tmap, const
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read_all() {
     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read_but_one() {
+    asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
 }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 

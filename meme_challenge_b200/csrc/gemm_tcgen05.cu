@@ -347,98 +347,120 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     if (warp == 0) {
         // ================= TMA producer =================
-        if (lane == 0) {
-            int s = 0;
-            uint32_t ph = 0;
-            // Side-input cursor: the next (tile, group) whose R box has not been requested. Boxes are
-            // requested opportunistically (try_wait on the group's empty barrier) from inside the
-            // operand loop and from its wait loops, never by blocking it: the epilogue that frees a
-            // group may itself be waiting, through the MMA warp, on operands only this thread loads.
-            int rt = unit0, rg = 0;
-            uint32_t rpar = 0;  // bit g: parity of the next use of group g's barriers
-            int t_cur = unit0;
-            int rm0 = 0, rn0 = 0;  // tile origin of the cursor (divisions only when the cursor moves)
-            auto r_origin = [&]() {
-                const int rrem = rt % tiles_mn;
-                rm0 = ((rrem % m_groups) * CLUSTER + cta_rank) * BLOCK_M;
-                rn0 = (rrem / m_groups) * BLOCK_N;
-            };
-            if (Cfg::HAS_R) r_origin();
-            auto r_pump = [&](bool block) {
-                if (!Cfg::HAS_R) return;
-                while (rt <= t_cur && rt < total_tiles) {
-                    if (rn0 + rg * 64 < g.N) {
-                        const uint32_t par = ((rpar >> rg) & 1u) ^ 1u;
-                        if (block) mbar_wait(&rempty[rg], par);
-                        else if (!mbar_try_wait(&rempty[rg], par)) return;
-                        mbar_arrive_expect_tx(&rfull[rg], Cfg::R_GROUP_BYTES);
-                        tma_load_2d(sR + rg * Cfg::R_GROUP_BYTES, &tmR, &rfull[rg], rn0 + 64 * rg, rm0);
-                        rpar ^= 1u << rg;
+        // The whole warp walks the loop with warp-uniform state and one elected lane issues the
+        // barrier arrivals and TMA requests: with uniform operands the requests compile to plain
+        // uniform-datapath UTMALDGs (no per-request R2UR + elect waterfall), which matters because at
+        // 128-wide tiles this single instruction stream must sustain one k-block every ~250 cycles.
+        const bool leader = elect_one();
+        const uint32_t sA_u = __shfl_sync(0xffffffffu, smem_u32(sA), 0);
+        const uint32_t sB_u = __shfl_sync(0xffffffffu, smem_u32(sB), 0);
+        const uint32_t sR_u = __shfl_sync(0xffffffffu, smem_u32(sR), 0);
+        const uint32_t full_u = __shfl_sync(0xffffffffu, smem_u32(full), 0);
+        const uint32_t rfull_u = __shfl_sync(0xffffffffu, smem_u32(rfull), 0);
+        int s = 0;
+        uint32_t ph = 0;
+        // Side-input cursor: the next (tile, group) whose R box has not been requested. Boxes are
+        // requested opportunistically (try_wait on the group's empty barrier) from inside the
+        // operand loop and from its wait loops, never by blocking it: the epilogue that frees a
+        // group may itself be waiting, through the MMA warp, on operands only this warp loads.
+        int rt = unit0, rg = 0;
+        uint32_t rpar = 0;  // bit g: parity of the next use of group g's barriers
+        int t_cur = unit0;
+        int rm0 = 0, rn0 = 0;  // tile origin of the cursor (divisions only when the cursor moves)
+        auto r_origin = [&]() {
+            const int rrem = rt % tiles_mn;
+            rm0 = ((rrem % m_groups) * CLUSTER + cta_rank) * BLOCK_M;
+            rn0 = (rrem / m_groups) * BLOCK_N;
+        };
+        if (Cfg::HAS_R) r_origin();
+        auto r_pump = [&](bool block) {
+            if (!Cfg::HAS_R) return;
+            while (rt <= t_cur && rt < total_tiles) {
+                if (rn0 + rg * 64 < g.N) {
+                    const uint32_t par = ((rpar >> rg) & 1u) ^ 1u;
+                    if (block) {
+                        mbar_wait(&rempty[rg], par);
+                    } else {
+                        const int ok = __shfl_sync(0xffffffffu, (int)mbar_try_wait(&rempty[rg], par), 0);
+                        if (!ok) return;
                     }
-                    if (++rg == NG) {
-                        rg = 0;
-                        rt += unit_stride;
-                        r_origin();
+                    if (leader) {
+                        mbar_arrive_expect_tx_u(rfull_u + rg * 8, Cfg::R_GROUP_BYTES);
+                        tma_load_2d_u(sR_u + rg * Cfg::R_GROUP_BYTES, &tmR, rfull_u + rg * 8, rn0 + 64 * rg, rm0);
                     }
+                    __syncwarp();
+                    rpar ^= 1u << rg;
                 }
-            };
-            for (int t = unit0; t < total_tiles; t += unit_stride) {
-                t_cur = t;
-                const int split = t / tiles_mn;
-                const int rem = t - split * tiles_mn;
-                const int m0 = ((rem % m_groups) * CLUSTER + cta_rank) * BLOCK_M;
-                const int n0 = (rem / m_groups) * BLOCK_N;
-                const int kb0 = split * g.kb_per_split;
-                const int kb1 = min(g.num_kb, kb0 + g.kb_per_split);
-                for (int kb = kb0; kb < kb1; ++kb) {
+                if (++rg == NG) {
+                    rg = 0;
+                    rt += unit_stride;
+                    r_origin();
+                }
+            }
+        };
+        for (int t = unit0; t < total_tiles; t += unit_stride) {
+            t_cur = t;
+            const int split = t / tiles_mn;
+            const int rem = t - split * tiles_mn;
+            const int m0 = ((rem % m_groups) * CLUSTER + cta_rank) * BLOCK_M;
+            const int n0 = (rem / m_groups) * BLOCK_N;
+            const int kb0 = split * g.kb_per_split;
+            const int kb1 = min(g.num_kb, kb0 + g.kb_per_split);
+            for (int kb = kb0; kb < kb1; ++kb) {
+                if (Cfg::HAS_R) {
                     while (!mbar_try_wait(&empty[s], ph ^ 1)) r_pump(false);
+                } else {
+                    mbar_wait(&empty[s], ph ^ 1);
+                }
+                if (leader) {
+                    const uint32_t fb = full_u + s * 8;
                     if (g.dbg_mode == 2) mbar_arrive(&full[s]);
-                    else mbar_arrive_expect_tx(&full[s], Cfg::STAGE_BYTES);
-                    uint8_t* a_dst = sA + s * Cfg::A_BYTES;
-                    uint8_t* b_dst = sB + s * Cfg::B_BYTES;
+                    else mbar_arrive_expect_tx_u(fb, Cfg::STAGE_BYTES);
+                    const uint32_t a_dst = sA_u + s * Cfg::A_BYTES;
+                    const uint32_t b_dst = sB_u + s * Cfg::B_BYTES;
                     if (g.dbg_mode == 2) {
                         // bring-up: no operand traffic, the MMAs run on whatever is in smem
                     } else if (!A_MN) {
-                        tma_load_2d(a_dst, &tmA, &full[s], kb * BLOCK_K, m0);
+                        tma_load_2d_u(a_dst, &tmA, fb, kb * BLOCK_K, m0);
                     } else {
 #pragma unroll
                         for (int i = 0; i < BLOCK_M / 64; ++i)
-                            tma_load_2d(a_dst + i * (BLOCK_K * 128), &tmA, &full[s], m0 + 64 * i,
-                                        kb * BLOCK_K);
+                            tma_load_2d_u(a_dst + i * (BLOCK_K * 128), &tmA, fb, m0 + 64 * i, kb * BLOCK_K);
                     }
                     if (g.dbg_mode == 2) {
                     } else if (CLUSTER == 1) {
                         if (!B_MN) {
-                            tma_load_2d(b_dst, &tmB, &full[s], kb * BLOCK_K, n0);
+                            tma_load_2d_u(b_dst, &tmB, fb, kb * BLOCK_K, n0);
                         } else {
 #pragma unroll
                             for (int i = 0; i < BLOCK_N / 64; ++i)
-                                tma_load_2d(b_dst + i * (BLOCK_K * 128), &tmB, &full[s], n0 + 64 * i,
-                                            kb * BLOCK_K);
+                                tma_load_2d_u(b_dst + i * (BLOCK_K * 128), &tmB, fb, n0 + 64 * i, kb * BLOCK_K);
                         }
                     } else {
                         // this CTA fetches its 1/CLUSTER slice of the B tile and multicasts it
+                        uint8_t* b_ptr = sB + s * Cfg::B_BYTES;
                         if (!B_MN) {
                             constexpr int ROWS = BLOCK_N / CLUSTER;
-                            tma_load_2d_mc(b_dst + cta_rank * (ROWS * 128), &tmB, &full[s], kb * BLOCK_K,
+                            tma_load_2d_mc(b_ptr + cta_rank * (ROWS * 128), &tmB, &full[s], kb * BLOCK_K,
                                            n0 + cta_rank * ROWS, MC_MASK);
                         } else {
                             constexpr int BOXES = BLOCK_N / 64 / CLUSTER;
 #pragma unroll
                             for (int j = 0; j < BOXES; ++j) {
                                 const int i = cta_rank * BOXES + j;
-                                tma_load_2d_mc(b_dst + i * (BLOCK_K * 128), &tmB, &full[s], n0 + 64 * i,
+                                tma_load_2d_mc(b_ptr + i * (BLOCK_K * 128), &tmB, &full[s], n0 + 64 * i,
                                                kb * BLOCK_K, MC_MASK);
                             }
                         }
                     }
-                    if (++s == STAGES) { s = 0; ph ^= 1; }
-                    r_pump(false);
                 }
+                __syncwarp();
+                if (++s == STAGES) { s = 0; ph ^= 1; }
+                if (Cfg::HAS_R) r_pump(false);
             }
-            r_pump(true);  // whatever side input is still outstanding (nothing else left to load)
-            DBG_STAMP(2);
         }
+        r_pump(true);  // whatever side input is still outstanding (nothing else left to load)
+        if (lane == 0) DBG_STAMP(2);
     } else if (warp == 1) {
         // ================= MMA issuer =================
         // Everything the issuing lane touches is kept warp-uniform (tile/stage counters, smem and
@@ -603,10 +625,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     uint8_t* dst = Cfg::HAS_R ? slot + q * (32 * 128) : stg;
                     tmem_ld_wait();                              // ra = columns col0 .. col0+31
                     tmem_ld_32x32(taddr + col0 + 32, rb);        // lands during the math on ra
-                    if (lane == 0) {
-                        bulk_wait_read_all();  // previous group's TMA store has finished reading smem
-                        if (Cfg::HAS_R && prev >= 0) mbar_arrive(&rempty[prev]);
-                    }
+                    // staging reuse: the previous group's TMA store must have finished reading smem
+                    // (side-input epilogues write in place, a different slot per group: no wait here)
+                    if (!Cfg::HAS_R && lane == 0) bulk_wait_read_all();
                     if (Cfg::HAS_R) {
                         mbar_wait(&rfull[gi], (rpar >> gi) & 1u);
                         rpar ^= 1u << gi;
@@ -642,6 +663,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         tma_store_2d(&tmC, dst, n0 + col0, m0 + q * 32);
                         if (Cfg::DUAL) tma_store_2d(&tmC2, stg + 4096, n0 + col0, m0 + q * 32);
                         bulk_commit();
+                        if (Cfg::HAS_R && prev >= 0) {
+                            // all but the store just committed have been read: the previous group's
+                            // side-input slot can be refilled for the next tile
+                            bulk_wait_read_but_one();
+                            mbar_arrive(&rempty[prev]);
+                        }
                     }
                     prev = gi;
                     gi = gn;

@@ -35,7 +35,7 @@ pooler_fwd_kernel(const bf16* __restrict__ h, size_t row_stride, const float* __
 }
 
 // blocks [0, ceil(H/8)):  dW[n,:] += sum_b dpre[b,n] h0[b,:] ; db[n] += sum_b dpre[b,n]
-// blocks [ceil(H/8), +B): dh0[b,:] = sum_n dpre[b,n] W[n,:]            (written as bf16)
+// blocks [ceil(H/8), +B*ceil(H/64)): dh0[b, 64-slice] = sum_n dpre[b,n] W[n, slice]   (written as bf16)
 // with dpre = dpooled * (1 - pooled^2).
 __global__ void __launch_bounds__(256)
 pooler_bwd_kernel(const float* __restrict__ dpooled, const float* __restrict__ pooled,
@@ -69,19 +69,28 @@ pooler_bwd_kernel(const float* __restrict__ dpooled, const float* __restrict__ p
         }
         if (lane == 0 && db) db[n] += bsum;
     } else {
-        const int b = blockIdx.x - nwb;
-        float* sd = sm;  // dpre[b, :]
+        // one block per (sample, 64-column slice): 4 groups of 64 threads stride over n, then reduce
+        const int nkb = (H + 63) / 64;
+        const int idx = blockIdx.x - nwb;
+        const int b = idx / nkb, k0 = (idx - b * nkb) * 64;
+        float* sd = sm;       // dpre[b, :]
+        float* red = sm + H;  // [4][64]
         for (int n = threadIdx.x; n < H; n += blockDim.x) {
             const float p = pooled[(size_t)b * H + n];
             sd[n] = dpooled[(size_t)b * H + n] * (1.0f - p * p);
         }
         __syncthreads();
-        for (int k = threadIdx.x; k < H; k += blockDim.x) {
-            float acc = 0.f;
+        const int kc = threadIdx.x & 63, ng = threadIdx.x >> 6;
+        const int k = k0 + kc;
+        float acc = 0.f;
+        if (k < H) {
 #pragma unroll 8
-            for (int n = 0; n < H; ++n) acc = fmaf(sd[n], W[(size_t)n * H + k], acc);
-            dh[(size_t)b * dh_row_stride + k] = __float2bfloat16(acc);
+            for (int n = ng; n < H; n += 4) acc = fmaf(sd[n], W[(size_t)n * H + k], acc);
         }
+        red[ng * 64 + kc] = acc;
+        __syncthreads();
+        if (ng == 0 && k < H)
+            dh[(size_t)b * dh_row_stride + k] = __float2bfloat16(red[kc] + red[64 + kc] + red[128 + kc] + red[192 + kc]);
     }
 }
 
@@ -178,7 +187,7 @@ extern "C" int b200u_pooler_bwd(const float* dpooled, const float* pooled, const
     cudaStream_t stream = (cudaStream_t)stream_;
     B200U_CHECK_ARG(dpooled && pooled && h && W && dW && dh && H % 4 == 0 && row_stride % 4 == 0, "pooler_bwd: bad arguments");
     if (B == 0) return B200U_OK;
-    launch_k(pooler_bwd_kernel, dim3((H + 7) / 8 + B), dim3(256), H * sizeof(float), stream, dpooled, pooled, (const bf16*)h, (size_t)row_stride, W, dW, db, (bf16*)dh, (size_t)dh_row_stride, B, H);
+    launch_k(pooler_bwd_kernel, dim3((H + 7) / 8 + B * ((H + 63) / 64)), dim3(256), (H + 256) * sizeof(float), stream, dpooled, pooled, (const bf16*)h, (size_t)row_stride, W, dW, db, (bf16*)dh, (size_t)dh_row_stride, B, H);
     B200U_CHECK_LAUNCH("pooler_bwd");
     return B200U_OK;
 }

@@ -122,111 +122,135 @@ layernorm_fwd_kernel(const TIn* __restrict__ x, const float* __restrict__ gamma,
 // Fused extras for the BertSelfOutput / BertOutput pattern x = dropout(dense) + residual
 // (model/layer.py:111-115,152-156): dz = dropout_mask(dx) (the dense output's grad, bf16) and
 // dbias += sum_rows dz. dx itself is the residual-branch grad.
+//
+// Layout: 20 warps per CTA, one CTA per SM, each warp owns ONE row per pass (2624 rows / 148 SMs
+// = 18 rows per CTA at the C2 shape, so a single pass): all of a row's loads are in flight at once
+// and nothing is carried in registers between rows. The per-row column contributions (dy*xhat, dy,
+// bf16(dz)) are staged in shared memory and summed down the columns by the same CTA, two columns
+// per thread, so the global fp32 accumulation costs 3*H atomics per CTA and no cross-warp
+// register reduction.
 // ---------------------------------------------------------------------------------------
-template <typename TX>
-__global__ void __launch_bounds__(256)
+constexpr int LNB_WARPS = 20;
+constexpr int LNB_THREADS = LNB_WARPS * 32;
+
+template <typename TX, int NVMAX>  // NVMAX: 16-byte vectors per lane (3 covers H <= 768, 4 covers H <= 1024)
+__global__ void __launch_bounds__(LNB_THREADS, 1)
 layernorm_bwd_kernel(const bf16* __restrict__ dy, const TX* __restrict__ x,
                      const float* __restrict__ mean, const float* __restrict__ rstd,
                      const float* __restrict__ gamma, bf16* __restrict__ dx, bf16* __restrict__ dz,
                      float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias,
-                     int M, int H, DropoutCfg drop, int drop_on_input) {
+                     int M, int H, int rows_per_cta, int rows_per_pass, DropoutCfg drop,
+                     int drop_on_input) {
     pdl_sync();
-    extern __shared__ float red[];  // [warps][H]
+    extern __shared__ __align__(16) float stage[];  // [3][rows_per_pass][H]: dy*xhat | dy | bf16(dz)
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const int nwarps = blockDim.x >> 5;
     const int nv = H >> 3;
     const uint64_t seed = load_seed(drop);
+    float* sG = stage;
+    float* sB = stage + (size_t)rows_per_pass * H;
+    float* sZ = stage + (size_t)2 * rows_per_pass * H;
 
-    float ag[LN_MAXV][8], ab[LN_MAXV][8], az[LN_MAXV][8];
-#pragma unroll
-    for (int i = 0; i < LN_MAXV; ++i)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) ag[i][j] = ab[i][j] = az[i][j] = 0.f;
+    const int r_begin = blockIdx.x * rows_per_cta;
+    const int r_end = min(M, r_begin + rows_per_cta);
+    const int c0 = 2 * threadIdx.x;  // this thread's column pair in the column pass
+    float cg0 = 0.f, cg1 = 0.f, cb0 = 0.f, cb1 = 0.f, cz0 = 0.f, cz1 = 0.f;
 
-    for (int row = blockIdx.x * nwarps + warp; row < M; row += gridDim.x * nwarps) {
-        const float mu = mean[row], rs = rstd[row];
-        float xh[LN_MAXV][8], gd[LN_MAXV][8];
-        float s1 = 0.f, s2 = 0.f;
+    for (int base = r_begin; base < r_end; base += rows_per_pass) {
+        const int row = base + warp;
+        if (warp < rows_per_pass && row < r_end) {
+            const float mu = mean[row], rs = rstd[row];
+            float xh[NVMAX][8], gd[NVMAX][8];
+            float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-        for (int i = 0; i < LN_MAXV; ++i) {
-            const int vi = lane + 32 * i;
-            if (vi < nv) {
-                float d[8], g[8];
-                load8(x + (size_t)row * H + vi * 8, xh[i]);
-                load8(dy + (size_t)row * H + vi * 8, d);
-                load8(gamma + vi * 8, g);
-                if (drop_on_input && drop.thresh16) {
-                    // y = dropout(LN(x)) (embedding modules): the incoming grad is masked first
-                    const uint32_t pbase = (uint32_t)(((size_t)row * H + vi * 8) >> 1);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        uint32_t h = rng_pair(seed, drop.stream, pbase + j);
-                        d[2 * j] = ((h & 0xffffu) >= drop.thresh16) ? d[2 * j] * drop.scale : 0.f;
-                        d[2 * j + 1] = ((h >> 16) >= drop.thresh16) ? d[2 * j + 1] * drop.scale : 0.f;
-                    }
-                }
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    xh[i][j] = (xh[i][j] - mu) * rs;
-                    ag[i][j] += d[j] * xh[i][j];
-                    ab[i][j] += d[j];
-                    gd[i][j] = d[j] * g[j];
-                    s1 += gd[i][j];
-                    s2 += gd[i][j] * xh[i][j];
+            for (int i = 0; i < NVMAX; ++i) {
+                const int vi = lane + 32 * i;
+                if (vi < nv) {
+                    load8(x + (size_t)row * H + vi * 8, xh[i]);
+                    load8(dy + (size_t)row * H + vi * 8, gd[i]);
                 }
             }
-        }
-        s1 = warp_sum(s1) / (float)H;
-        s2 = warp_sum(s2) / (float)H;
 #pragma unroll
-        for (int i = 0; i < LN_MAXV; ++i) {
-            const int vi = lane + 32 * i;
-            if (vi < nv) {
-                float o[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) o[j] = rs * (gd[i][j] - s1 - xh[i][j] * s2);
-                if (dx) store8(dx + (size_t)row * H + vi * 8, o);
-                if (dz) {
-                    if (drop.thresh16 && !drop_on_input) {
+            for (int i = 0; i < NVMAX; ++i) {
+                const int vi = lane + 32 * i;
+                if (vi < nv) {
+                    float g[8], a[8];
+                    load8(gamma + vi * 8, g);
+                    if (drop_on_input && drop.thresh16) {
+                        // y = dropout(LN(x)) (embedding modules): the incoming grad is masked first
                         const uint32_t pbase = (uint32_t)(((size_t)row * H + vi * 8) >> 1);
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             uint32_t h = rng_pair(seed, drop.stream, pbase + j);
-                            o[2 * j] = ((h & 0xffffu) >= drop.thresh16) ? o[2 * j] * drop.scale : 0.f;
-                            o[2 * j + 1] = ((h >> 16) >= drop.thresh16) ? o[2 * j + 1] * drop.scale : 0.f;
+                            gd[i][2 * j] = ((h & 0xffffu) >= drop.thresh16) ? gd[i][2 * j] * drop.scale : 0.f;
+                            gd[i][2 * j + 1] = ((h >> 16) >= drop.thresh16) ? gd[i][2 * j + 1] * drop.scale : 0.f;
                         }
                     }
-                    store8(dz + (size_t)row * H + vi * 8, o);
-                }
-                if (dbias) {
-                    // column sums of the bf16-rounded dz: exactly what the wgrad GEMM consumes
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) az[i][j] += __bfloat162float(__float2bfloat16(o[j]));
+                    for (int j = 0; j < 8; ++j) {
+                        xh[i][j] = (xh[i][j] - mu) * rs;
+                        a[j] = gd[i][j] * xh[i][j];
+                    }
+                    store8(sG + (size_t)warp * H + vi * 8, a);
+                    store8(sB + (size_t)warp * H + vi * 8, gd[i]);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        gd[i][j] *= g[j];
+                        s1 += gd[i][j];
+                        s2 += gd[i][j] * xh[i][j];
+                    }
+                }
+            }
+            s1 = warp_sum(s1) / (float)H;
+            s2 = warp_sum(s2) / (float)H;
+#pragma unroll
+            for (int i = 0; i < NVMAX; ++i) {
+                const int vi = lane + 32 * i;
+                if (vi < nv) {
+                    float o[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) o[j] = rs * (gd[i][j] - s1 - xh[i][j] * s2);
+                    if (dx) store8(dx + (size_t)row * H + vi * 8, o);
+                    if (dz) {
+                        if (drop.thresh16 && !drop_on_input) {
+                            const uint32_t pbase = (uint32_t)(((size_t)row * H + vi * 8) >> 1);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                uint32_t h = rng_pair(seed, drop.stream, pbase + j);
+                                o[2 * j] = ((h & 0xffffu) >= drop.thresh16) ? o[2 * j] * drop.scale : 0.f;
+                                o[2 * j + 1] = ((h >> 16) >= drop.thresh16) ? o[2 * j + 1] * drop.scale : 0.f;
+                            }
+                        }
+                        store8(dz + (size_t)row * H + vi * 8, o);
+                    }
+                    if (dbias) {
+                        // column sums of the bf16-rounded dz: exactly what the wgrad GEMM consumes
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) o[j] = __bfloat162float(__float2bfloat16(o[j]));
+                        store8(sZ + (size_t)warp * H + vi * 8, o);
+                    }
                 }
             }
         }
+        __syncthreads();
+        const int nrows = min(rows_per_pass, r_end - base);
+        if (c0 < H) {
+            for (int r = 0; r < nrows; ++r) {
+                const float2 a = *reinterpret_cast<const float2*>(sG + (size_t)r * H + c0);
+                const float2 bb = *reinterpret_cast<const float2*>(sB + (size_t)r * H + c0);
+                cg0 += a.x; cg1 += a.y; cb0 += bb.x; cb1 += bb.y;
+                if (dbias) {
+                    const float2 z = *reinterpret_cast<const float2*>(sZ + (size_t)r * H + c0);
+                    cz0 += z.x; cz1 += z.y;
+                }
+            }
+        }
+        __syncthreads();  // staging is rewritten by the next pass
     }
-
-    // cross-warp reduction of the three column accumulators, one at a time through smem
-    for (int which = 0; which < 3; ++which) {
-        float* dst = which == 0 ? dgamma : (which == 1 ? dbeta : dbias);
-        if (!dst) continue;  // uniform
-        __syncthreads();
-#pragma unroll
-        for (int i = 0; i < LN_MAXV; ++i) {
-            const int vi = lane + 32 * i;
-            if (vi < nv)
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    red[warp * H + vi * 8 + j] = which == 0 ? ag[i][j] : (which == 1 ? ab[i][j] : az[i][j]);
-        }
-        __syncthreads();
-        for (int c = threadIdx.x; c < H; c += blockDim.x) {
-            float s = 0.f;
-            for (int w = 0; w < nwarps; ++w) s += red[w * H + c];
-            atomicAdd(dst + c, s);
-        }
+    if (c0 < H && r_begin < r_end) {
+        if (dgamma) { atomicAdd(dgamma + c0, cg0); atomicAdd(dgamma + c0 + 1, cg1); }
+        if (dbeta) { atomicAdd(dbeta + c0, cb0); atomicAdd(dbeta + c0 + 1, cb1); }
+        if (dbias) { atomicAdd(dbias + c0, cz0); atomicAdd(dbias + c0 + 1, cz1); }
     }
 }
 
@@ -407,13 +431,31 @@ extern "C" int b200u_layernorm_bwd(const void* dy, const void* x, int x_dtype, c
     b200u_dropout_t nodrop = {nullptr, 0, 0.f};
     DropoutCfg dc = make_drop(drop ? *drop : nodrop);
     B200U_CHECK_ARG(dc.thresh16 == 0 || dc.seed_ptr, "layernorm_bwd: dropout needs seed_ptr");
-    int grid = (M + 7) / 8;
+    // one row per warp per pass; as many rows per pass as the staging tile [3][rows][H] fp32 allows
+    int rows_per_pass = (int)((size_t)200 * 1024 / ((size_t)3 * H * sizeof(float)));
+    if (rows_per_pass > LNB_WARPS) rows_per_pass = LNB_WARPS;
+    int grid = (M + rows_per_pass - 1) / rows_per_pass;
     if (grid > num_sms()) grid = num_sms();
-    const size_t smem = (size_t)8 * H * sizeof(float);
-    if (x_dtype == B200U_BF16)
-        launch_k(layernorm_bwd_kernel<bf16>, dim3(grid), dim3(256), smem, stream, (const bf16*)dy, (const bf16*)x, mean, rstd, gamma, (bf16*)dx, (bf16*)dz, dgamma, dbeta, dbias, M, H, dc, drop_on_input);
-    else if (x_dtype == B200U_F32)
-        launch_k(layernorm_bwd_kernel<float>, dim3(grid), dim3(256), smem, stream, (const bf16*)dy, (const float*)x, mean, rstd, gamma, (bf16*)dx, (bf16*)dz, dgamma, dbeta, dbias, M, H, dc, drop_on_input);
+    const int rows_per_cta = (M + grid - 1) / grid;
+    grid = (M + rows_per_cta - 1) / rows_per_cta;
+    const size_t smem = (size_t)3 * rows_per_pass * H * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+        B200U_CHECK_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<bf16, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        B200U_CHECK_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<bf16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        B200U_CHECK_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<float, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        B200U_CHECK_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<float, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set = true;
+    }
+    const bool narrow = H <= 768;
+#define LNB_LAUNCH(TX, NV) \
+    launch_k(layernorm_bwd_kernel<TX, NV>, dim3(grid), dim3(LNB_THREADS), smem, stream, (const bf16*)dy, (const TX*)x, mean, rstd, gamma, (bf16*)dx, (bf16*)dz, dgamma, dbeta, dbias, M, H, rows_per_cta, rows_per_pass, dc, drop_on_input)
+    if (x_dtype == B200U_BF16) {
+        if (narrow) LNB_LAUNCH(bf16, 3); else LNB_LAUNCH(bf16, 4);
+    } else if (x_dtype == B200U_F32) {
+        if (narrow) LNB_LAUNCH(float, 3); else LNB_LAUNCH(float, 4);
+    }
+#undef LNB_LAUNCH
     else
         B200U_CHECK_ARG(false, "layernorm_bwd: unsupported x dtype %d", x_dtype);
     B200U_CHECK_LAUNCH("layernorm_bwd");
