@@ -86,24 +86,37 @@ __device__ __forceinline__ void mma_x(float (&o)[8][4], uint32_t a0, uint32_t a1
 // cooperative ASYNC load (cp.async, 16 B per request, all requests in flight at once) of `rows` rows
 // x 64 bf16 from a [*, ld] matrix into a swizzled smem tile, zero-filling rows >= valid. Callers
 // finish with load_tiles_wait() before the __syncthreads() that publishes the tiles.
-__device__ __forceinline__ void load_tile(bf16* dst, const bf16* src, int ld, int valid, int rows,
+__device__ __forceinline__ void load_rows(bf16* dst, const bf16* src, int ld, int valid, int rb, int re,
                                           int tid, int nthreads, int valid_chunks = 8) {
-    // a thread keeps its 16-byte chunk column and walks the rows in steps of nthreads/8 (a multiple
-    // of 8), so the swizzled chunk, both strides and the chunk predicate are loop invariant
+    // rows [rb, re) of the tile. A thread keeps its 16-byte chunk column and walks the rows in steps
+    // of nthreads/8, so the source stride and the chunk predicate are loop invariant (and, when the
+    // step is a multiple of 8 rows, so is the swizzled chunk).
     const int ch = tid & 7;
     const int rstep = nthreads >> 3;
-    int r = tid >> 3;
-    bf16* d = dst + r * HD + ((ch ^ (r & 7)) << 3);
+    int r = rb + (tid >> 3);
     const bf16* s = src + (size_t)r * ld + ch * 8;
     const size_t sstep = (size_t)rstep * ld;
     const bool chunk_ok = ch < valid_chunks;
-    for (; r < rows; r += rstep, d += rstep * HD, s += sstep) {
+    for (; r < re; r += rstep, s += sstep) {
+        bf16* d = dst + r * HD + ((ch ^ (r & 7)) << 3);
         if (chunk_ok && r < valid) {
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(d)), "l"(s) : "memory");
         } else {
             *reinterpret_cast<uint4*>(d) = make_uint4(0, 0, 0, 0);
         }
     }
+}
+__device__ __forceinline__ void load_tile(bf16* dst, const bf16* src, int ld, int valid, int rows,
+                                          int tid, int nthreads, int valid_chunks = 8) {
+    load_rows(dst, src, ld, valid, 0, rows, tid, nthreads, valid_chunks);
+}
+__device__ __forceinline__ void load_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+// wait until at most `pending` of this thread's committed cp.async groups are still in flight
+__device__ __forceinline__ void load_wait_pending(int pending) {
+    if (pending <= 0) asm volatile("cp.async.wait_group 0;" ::: "memory");
+    else if (pending == 1) asm volatile("cp.async.wait_group 1;" ::: "memory");
+    else if (pending == 2) asm volatile("cp.async.wait_group 2;" ::: "memory");
+    else asm volatile("cp.async.wait_group 3;" ::: "memory");
 }
 __device__ __forceinline__ void load_tiles_wait() {
     asm volatile("cp.async.commit_group;" ::: "memory");
@@ -143,19 +156,23 @@ attn_fwd_kernel(const bf16* __restrict__ qkv, const float* __restrict__ mask, bf
     const int ld = 3 * H;
     const bf16* base = qkv + (size_t)b * L * ld + h * HD;
 
+    // K/V arrive in 64-key chunks, one cp.async group each (the first also carries Q): the sweep
+    // below starts on chunk 0 while the later chunks are still in flight
+    const int nchunks = (L + 63) >> 6;
     load_tile(sQ, base + (size_t)q0 * ld, ld, L - q0, TQ, tid, 128);
-    load_tile(sK, base + H, ld, L, LP, tid, 128);
-    load_tile(sV, base + 2 * H, ld, L, LP, tid, 128);
+    for (int c = 0; c < nchunks; ++c) {
+        const int rb = c * 64, re = min(LP, rb + 64);
+        load_rows(sK, base + H, ld, L, rb, re, tid, 128);
+        load_rows(sV, base + 2 * H, ld, L, rb, re, tid, 128);
+        load_commit();
+    }
     // additive mask in the log2 domain, padded with -inf to the 64-key chunks the loop sweeps
     const int LP64 = (L + 63) & ~63;
     for (int j = tid; j < LP64; j += 128) sM[j] = (j < L) ? mask[(size_t)b * L + j] * LOG2E : -INFINITY;
-    load_tiles_wait();
-    __syncthreads();
 
     const int r0 = q0 + warp * 16;
-    if (r0 >= L) return;
+    const bool active = r0 < L;  // warps past the end of the sequence only take part in the barriers
     uint32_t qa[4][4];
-    load_a_frags(sQ, warp * 16, lane, qa);
 
     const int g = lane >> 2, t2 = (lane & 3) * 2;
     const int i0 = r0 + g, i1 = r0 + g + 8;
@@ -170,6 +187,10 @@ attn_fwd_kernel(const bf16* __restrict__ qkv, const float* __restrict__ mask, bf
     for (int nt = 0; nt < 8; ++nt) o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f;
 
     for (int c0 = 0; c0 < L; c0 += 64) {
+        load_wait_pending(nchunks - 1 - (c0 >> 6));
+        __syncthreads();
+        if (!active) continue;
+        if (c0 == 0) load_a_frags(sQ, warp * 16, lane, qa);
         float s[8][4];
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
@@ -223,6 +244,7 @@ attn_fwd_kernel(const bf16* __restrict__ qkv, const float* __restrict__ mask, bf
             }
         }
     }
+    if (!active) return;
     l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
     l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
     l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
@@ -275,10 +297,16 @@ attn_bwd_dq_kernel(const bf16* __restrict__ qkv, const float* __restrict__ mask,
     const bf16* dO = dctx + (size_t)b * L * H + h * HD;
     const bf16* O = ctx + (size_t)b * L * H + h * HD;
 
+    // Q/dO tile + K/V in 64-key chunks, one cp.async group per chunk (the first carries Q and dO)
+    const int nchunks = (LP + 63) >> 6;
     load_tile(sQ, base + (size_t)t0 * ld, ld, L - t0, TQ, tid, 128);
     load_tile(sdO, dO + (size_t)t0 * H, H, L - t0, TQ, tid, 128);
-    load_tile(sK, base + H, ld, L, LP, tid, 128);
-    load_tile(sV, base + 2 * H, ld, L, LP, tid, 128);
+    for (int c = 0; c < nchunks; ++c) {
+        const int rb = c * 64, re = min(LP, rb + 64);
+        load_rows(sK, base + H, ld, L, rb, re, tid, 128);
+        load_rows(sV, base + 2 * H, ld, L, rb, re, tid, 128);
+        load_commit();
+    }
     for (int j = tid; j < LP; j += 128) sM2[j] = (j < L) ? mask[(size_t)b * L + j] * LOG2E : -INFINITY;
     for (int i = tid >> 3; i < TQ; i += 16) {  // D_i and lse_i of the tile rows: 8 threads per row
         const int gi = t0 + i;
@@ -303,19 +331,13 @@ attn_bwd_dq_kernel(const bf16* __restrict__ qkv, const float* __restrict__ mask,
             sL2[i] = (gi < L) ? lse[(size_t)bh * L + gi] * LOG2E : 0.f;
         }
     }
-    load_tiles_wait();
-    __syncthreads();
-
     const int r0 = t0 + warp * 16;
-    if (r0 >= L) return;
+    const bool active = r0 < L;  // warps past the end of the sequence only take part in the barriers
     const uint32_t key = drop.thresh16 ? attn_key(load_seed(drop), drop.stream) : 0u;
     const int g = lane >> 2, t2 = (lane & 3) * 2;
     const int x0 = r0 + g, x1 = r0 + g + 8;
     uint32_t qa[4][4], da[4][4];
-    load_a_frags(sQ, warp * 16, lane, qa);
-    load_a_frags(sdO, warp * 16, lane, da);
-    const float la = sL2[warp * 16 + g], lb = sL2[warp * 16 + g + 8];
-    const float Da = sD[warp * 16 + g], Db = sD[warp * 16 + g + 8];
+    float la = 0.f, lb = 0.f, Da = 0.f, Db = 0.f;
     const uint32_t pb0 = attn_pair_base(bh, x0, L), pb1 = attn_pair_base(bh, x1, L);
     constexpr float SC = 0.125f * LOG2E;
     bf16* pP0 = scrP + ((size_t)bh * L + x0) * LP;
@@ -326,6 +348,17 @@ attn_bwd_dq_kernel(const bf16* __restrict__ qkv, const float* __restrict__ mask,
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) dq[nt][0] = dq[nt][1] = dq[nt][2] = dq[nt][3] = 0.f;
     for (int c0 = 0; c0 < LP; c0 += 32) {
+        if ((c0 & 63) == 0) {
+            load_wait_pending(nchunks - 1 - (c0 >> 6));
+            __syncthreads();
+            if (c0 == 0 && active) {
+                load_a_frags(sQ, warp * 16, lane, qa);
+                load_a_frags(sdO, warp * 16, lane, da);
+                la = sL2[warp * 16 + g]; lb = sL2[warp * 16 + g + 8];
+                Da = sD[warp * 16 + g]; Db = sD[warp * 16 + g + 8];
+            }
+        }
+        if (!active) continue;
         float s[4][4], dp[4][4];
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) {
@@ -378,6 +411,7 @@ attn_bwd_dq_kernel(const bf16* __restrict__ qkv, const float* __restrict__ mask,
             }
         }
     }
+    if (!active) return;
     bf16* dbase = dqkv + (size_t)b * L * ld + h * HD;
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
@@ -416,16 +450,21 @@ attn_bwd_dkv_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dctx,
     const int ld = 3 * H;
     const bf16* base = qkv + (size_t)b * L * ld + h * HD;
     const bf16* dO = dctx + (size_t)b * L * H + h * HD;
-    load_tile(sQ, base, ld, L, LP, tid, 128);
-    load_tile(sdO, dO, H, L, LP, tid, 128);
+    // all four tiles are indexed by QUERY row (the reduction index here): load them in 64-row
+    // chunks, one cp.async group each, and start the products on chunk 0 while the rest is in flight.
     // key columns t0..t0+63 of every query row; columns >= LP (last tile) are zero-filled
     const int vch = min(8, (LP - t0) >> 3);
-    load_tile(sP, scrP + (size_t)bh * L * LP + t0, LP, L, LP, tid, 128, vch);
-    load_tile(sS, scrS + (size_t)bh * L * LP + t0, LP, L, LP, tid, 128, vch);
-    load_tiles_wait();
-    __syncthreads();
+    const int nchunks = (LP + 63) >> 6;
+    for (int c = 0; c < nchunks; ++c) {
+        const int rb = c * 64, re = min(LP, rb + 64);
+        load_rows(sQ, base, ld, L, rb, re, tid, 128);
+        load_rows(sdO, dO, H, L, rb, re, tid, 128);
+        load_rows(sP, scrP + (size_t)bh * L * LP + t0, LP, L, rb, re, tid, 128, vch);
+        load_rows(sS, scrS + (size_t)bh * L * LP + t0, LP, L, rb, re, tid, 128, vch);
+        load_commit();
+    }
     const int r0 = t0 + warp * 16;
-    if (r0 >= L) return;
+    const bool active = r0 < L;  // warps past the end of the sequence only take part in the barriers
     float dk[8][4], dv[8][4];
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
@@ -433,9 +472,15 @@ attn_bwd_dkv_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dctx,
         dv[nt][0] = dv[nt][1] = dv[nt][2] = dv[nt][3] = 0.f;
     }
     for (int k0 = 0; k0 < LP; k0 += 16) {
+        if ((k0 & 63) == 0) {
+            load_wait_pending(nchunks - 1 - (k0 >> 6));
+            __syncthreads();
+        }
+        if (!active) continue;
         mma_tn(dv, sP, sdO, warp * 16, k0, lane);  // dV += Pdᵀ·dO
         mma_tn(dk, sS, sQ, warp * 16, k0, lane);   // dK += dSᵀ·Q
     }
+    if (!active) return;
     const int g = lane >> 2, t2 = (lane & 3) * 2;
     const int x0 = r0 + g, x1 = r0 + g + 8;
     bf16* dbase = dqkv + (size_t)b * L * ld + h * HD;
@@ -446,6 +491,186 @@ attn_bwd_dkv_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dctx,
             *reinterpret_cast<uint32_t*>(dbase + (size_t)x0 * ld + 2 * H + nt * 8 + t2) = pack_bf16(dv[nt][0], dv[nt][1]);
         }
         if (x1 < L) {
+            *reinterpret_cast<uint32_t*>(dbase + (size_t)x1 * ld + H + nt * 8 + t2) = pack_bf16(dk[nt][2], dk[nt][3]);
+            *reinterpret_cast<uint32_t*>(dbase + (size_t)x1 * ld + 2 * H + nt * 8 + t2) = pack_bf16(dv[nt][2], dv[nt][3]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Backward, fused variant for joint sequences up to 176 (the C2 shape: L = 164): ONE CTA per
+// (sample, head), ceil(L/16) warps. Q, K, V, dO and the whole Pd / dS matrices (bf16, three
+// 64-key column tiles each) live in shared memory (222 KB), so nothing is recomputed, nothing goes
+// through a global scratch buffer and every input row is read from L2 exactly once:
+//   phase 1 (warp = 16 query rows): S, dPd in 32-key chunks -> Pd, dS tiles in smem ; dQ = dS·K
+//   phase 2 (warp = 16 key rows)  : dV = Pdᵀ·dO ; dK = dSᵀ·Q  (ldmatrix.trans over the smem tiles)
+// ---------------------------------------------------------------------------------------
+constexpr int FUSED_MAX_LP = 176;
+
+__global__ void __launch_bounds__(FUSED_MAX_LP * 2, 1)
+attn_bwd_fused_kernel(const bf16* __restrict__ qkv, const float* __restrict__ mask,
+                      const bf16* __restrict__ ctx, const bf16* __restrict__ dctx,
+                      const float* __restrict__ lse, bf16* __restrict__ dqkv, int L, int LP, int nh,
+                      int H, DropoutCfg drop) {
+    pdl_sync();
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    const int TILE = LP * HD;  // elements of one [LP][64] tile
+    bf16* sQ = reinterpret_cast<bf16*>(smem_raw);
+    bf16* sK = sQ + TILE;
+    bf16* sV = sK + TILE;
+    bf16* sdO = sV + TILE;
+    bf16* sP = sdO + TILE;      // 3 tiles: keys 0-63 | 64-127 | 128-191, rows = queries
+    bf16* sS = sP + 3 * TILE;   // 3 tiles, same layout
+    float* sM2 = reinterpret_cast<float*>(sS + 3 * TILE);  // additive mask * log2(e), -inf past L (192 entries)
+    float* sL2 = sM2 + 192;                                // lse * log2(e) per query row
+    float* sD = sL2 + LP;                                  // D_i = sum_d dO[i,d] O[i,d]
+
+    const int bh = blockIdx.x, b = bh / nh, h = bh - b * nh;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nthreads = blockDim.x;
+    const int ld = 3 * H;
+    const bf16* base = qkv + (size_t)b * L * ld + h * HD;
+    const bf16* dO = dctx + (size_t)b * L * H + h * HD;
+    const bf16* O = ctx + (size_t)b * L * H + h * HD;
+
+    // group 0: Q, dO and the first 64 keys of K/V; then one cp.async group per further 64-key chunk
+    const int nchunks = (LP + 63) >> 6;
+    load_rows(sQ, base, ld, L, 0, LP, tid, nthreads);
+    load_rows(sdO, dO, H, L, 0, LP, tid, nthreads);
+    for (int c = 0; c < nchunks; ++c) {
+        const int rb = c * 64, re = min(LP, rb + 64);
+        load_rows(sK, base + H, ld, L, rb, re, tid, nthreads);
+        load_rows(sV, base + 2 * H, ld, L, rb, re, tid, nthreads);
+        load_commit();
+    }
+    for (int j = tid; j < 192; j += nthreads) sM2[j] = (j < L) ? mask[(size_t)b * L + j] * LOG2E : -INFINITY;
+    for (int i = tid >> 3; i < LP; i += nthreads >> 3) {  // D_i and lse_i: 8 threads per row
+        float d = 0.f;
+        if (i < L) {
+            const int ch = tid & 7;
+            uint4 ov = *reinterpret_cast<const uint4*>(O + (size_t)i * H + ch * 8);
+            uint4 dv = *reinterpret_cast<const uint4*>(dO + (size_t)i * H + ch * 8);
+            const uint32_t* op = &ov.x;
+            const uint32_t* dp = &dv.x;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float2 x = unpack_bf16(op[k]), y = unpack_bf16(dp[k]);
+                d += x.x * y.x + x.y * y.y;
+            }
+        }
+        d += __shfl_xor_sync(0xffffffffu, d, 1);
+        d += __shfl_xor_sync(0xffffffffu, d, 2);
+        d += __shfl_xor_sync(0xffffffffu, d, 4);
+        if ((tid & 7) == 0) {
+            sD[i] = d;
+            sL2[i] = (i < L) ? lse[(size_t)bh * L + i] * LOG2E : 0.f;
+        }
+    }
+
+    // ---------------- phase 1: this warp's 16 query rows against all keys ----------------
+    const int r0 = warp * 16;
+    const uint32_t key = drop.thresh16 ? attn_key(load_seed(drop), drop.stream) : 0u;
+    const int g = lane >> 2, t2 = (lane & 3) * 2;
+    const int x0 = r0 + g, x1 = r0 + g + 8;
+    const bool v0 = x0 < L, v1 = x1 < L;
+    uint32_t qa[4][4], da[4][4];
+    float la = 0.f, lb = 0.f, Da = 0.f, Db = 0.f;
+    const uint32_t pb0 = attn_pair_base(bh, x0, L), pb1 = attn_pair_base(bh, x1, L);
+    constexpr float SC = 0.125f * LOG2E;
+    float dq[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) dq[nt][0] = dq[nt][1] = dq[nt][2] = dq[nt][3] = 0.f;
+    for (int c0 = 0; c0 < LP; c0 += 32) {
+        if ((c0 & 63) == 0) {
+            load_wait_pending(nchunks - 1 - (c0 >> 6));
+            __syncthreads();
+            if (c0 == 0) {
+                load_a_frags(sQ, r0, lane, qa);
+                load_a_frags(sdO, r0, lane, da);
+                la = sL2[x0]; lb = sL2[x1];
+                Da = sD[x0]; Db = sD[x1];
+            }
+        }
+        // (when LP % 32 == 16 the last chunk also writes 16 all-zero key columns past LP: they stay
+        //  inside the 64-wide tile and are never read by phase 2)
+        bf16* tP = sP + (c0 >> 6) * TILE;
+        bf16* tS = sS + (c0 >> 6) * TILE;
+        float s[4][4], dp[4][4];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+            dp[nt][0] = dp[nt][1] = dp[nt][2] = dp[nt][3] = 0.f;
+        }
+#pragma unroll
+        for (int np = 0; np < 2; ++np) {
+            if (c0 + np * 16 < LP) {
+                mma_xt(s[2 * np], s[2 * np + 1], qa, sK, c0 + np * 16, lane);    // Q·Kᵀ
+                mma_xt(dp[2 * np], dp[2 * np + 1], da, sV, c0 + np * 16, lane);  // dO·Vᵀ
+            }
+        }
+#pragma unroll
+        for (int np = 0; np < 2; ++np) {
+            uint32_t dsp[2][2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int nt = 2 * np + e;
+                const int j = c0 + nt * 8 + t2;
+                const float ma = sM2[j], mb = sM2[j + 1];
+                // rows / columns outside the sequence contribute exact zeros (mask = -inf past L)
+                const float p0 = v0 ? ex2_approx(fmaf(s[nt][0], SC, ma) - la) : 0.f;
+                const float p1 = v0 ? ex2_approx(fmaf(s[nt][1], SC, mb) - la) : 0.f;
+                const float p2 = v1 ? ex2_approx(fmaf(s[nt][2], SC, ma) - lb) : 0.f;
+                const float p3 = v1 ? ex2_approx(fmaf(s[nt][3], SC, mb) - lb) : 0.f;
+                float k0 = 1.f, k1 = 1.f, k2 = 1.f, k3 = 1.f;
+                if (drop.thresh16) {
+                    const uint32_t jp = (uint32_t)j >> 1;
+                    const uint32_t h0 = attn_rng(key, pb0 + jp), h1 = attn_rng(key, pb1 + jp);
+                    k0 = ((h0 & 0xffffu) >= drop.thresh16) ? drop.scale : 0.f;
+                    k1 = ((h0 >> 16) >= drop.thresh16) ? drop.scale : 0.f;
+                    k2 = ((h1 & 0xffffu) >= drop.thresh16) ? drop.scale : 0.f;
+                    k3 = ((h1 >> 16) >= drop.thresh16) ? drop.scale : 0.f;
+                }
+                dsp[e][0] = pack_bf16(p0 * (dp[nt][0] * k0 - Da) * 0.125f, p1 * (dp[nt][1] * k1 - Da) * 0.125f);
+                dsp[e][1] = pack_bf16(p2 * (dp[nt][2] * k2 - Db) * 0.125f, p3 * (dp[nt][3] * k3 - Db) * 0.125f);
+                const int cc = j & 63;
+                const int o0 = sw_off(x0, cc >> 3) + (cc & 7), o1 = sw_off(x1, cc >> 3) + (cc & 7);
+                *reinterpret_cast<uint32_t*>(tP + o0) = pack_bf16(p0 * k0, p1 * k1);
+                *reinterpret_cast<uint32_t*>(tP + o1) = pack_bf16(p2 * k2, p3 * k3);
+                *reinterpret_cast<uint32_t*>(tS + o0) = dsp[e][0];
+                *reinterpret_cast<uint32_t*>(tS + o1) = dsp[e][1];
+            }
+            if (c0 + np * 16 < LP) mma_x(dq, dsp[0][0], dsp[0][1], dsp[1][0], dsp[1][1], sK, c0 + np * 16, lane);
+        }
+    }
+    bf16* dbase = dqkv + (size_t)b * L * ld + h * HD;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+        if (v0) *reinterpret_cast<uint32_t*>(dbase + (size_t)x0 * ld + nt * 8 + t2) = pack_bf16(dq[nt][0], dq[nt][1]);
+        if (v1) *reinterpret_cast<uint32_t*>(dbase + (size_t)x1 * ld + nt * 8 + t2) = pack_bf16(dq[nt][2], dq[nt][3]);
+    }
+    __syncthreads();  // every warp's rows of Pd / dS are in shared memory
+
+    // ---------------- phase 2: this warp's 16 key rows, reduction over all queries ----------------
+    float dk[8][4], dv[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+        dk[nt][0] = dk[nt][1] = dk[nt][2] = dk[nt][3] = 0.f;
+        dv[nt][0] = dv[nt][1] = dv[nt][2] = dv[nt][3] = 0.f;
+    }
+    const bf16* tP2 = sP + (warp >> 2) * TILE;
+    const bf16* tS2 = sS + (warp >> 2) * TILE;
+    const int m0 = (warp & 3) * 16;
+    for (int k0 = 0; k0 < LP; k0 += 16) {
+        mma_tn(dv, tP2, sdO, m0, k0, lane);  // dV += Pdᵀ·dO
+        mma_tn(dk, tS2, sQ, m0, k0, lane);   // dK += dSᵀ·Q
+    }
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+        if (v0) {
+            *reinterpret_cast<uint32_t*>(dbase + (size_t)x0 * ld + H + nt * 8 + t2) = pack_bf16(dk[nt][0], dk[nt][1]);
+            *reinterpret_cast<uint32_t*>(dbase + (size_t)x0 * ld + 2 * H + nt * 8 + t2) = pack_bf16(dv[nt][0], dv[nt][1]);
+        }
+        if (v1) {
             *reinterpret_cast<uint32_t*>(dbase + (size_t)x1 * ld + H + nt * 8 + t2) = pack_bf16(dk[nt][2], dk[nt][3]);
             *reinterpret_cast<uint32_t*>(dbase + (size_t)x1 * ld + 2 * H + nt * 8 + t2) = pack_bf16(dv[nt][2], dv[nt][3]);
         }
@@ -492,6 +717,18 @@ static int launch_bwd(const void* qkv, const float* mask, const void* ctx, const
     if (smem2 > set2) {
         B200U_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
         set2 = smem2;
+    }
+    if (LP <= FUSED_MAX_LP) {
+        // one CTA per (sample, head): Q, K, V, dO (4 tiles), Pd and dS (3 tiles each) + mask / lse / D
+        const size_t smem = (size_t)10 * LP * HD * 2 + (size_t)(192 + 2 * LP) * 4;
+        static size_t set3 = 0;
+        if (smem > set3) {
+            B200U_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            set3 = smem;
+        }
+        launch_k(attn_bwd_fused_kernel, dim3(B * nh), dim3(LP * 2), smem, stream, (const bf16*)qkv, mask, (const bf16*)ctx, (const bf16*)dctx, lse, (bf16*)dqkv, L, LP, nh, H, dc);
+        B200U_CHECK_LAUNCH("attn_bwd_fused_kernel");
+        return B200U_OK;
     }
     const dim3 grid(B * nh, (L + TQ - 1) / TQ);
     launch_k(attn_bwd_dq_kernel, dim3(grid), dim3(128), smem1, stream, (const bf16*)qkv, mask, (const bf16*)ctx, (const bf16*)dctx, lse, (bf16*)dqkv, scrP, scrS, L, LP, nh, H, dc);

@@ -388,6 +388,86 @@ def test_grad_accumulation_and_zero_grad_set_to_none():
     assert torch.isfinite(l_after).all()
 
 
+LARGE_SHAPES = dict(vocab_size=28996, hidden_size=1024, num_hidden_layers=2, num_attention_heads=16,
+                    intermediate_size=4096, hidden_act="gelu", hidden_dropout_prob=0.1,
+                    attention_probs_dropout_prob=0.1, max_position_embeddings=512, type_vocab_size=2,
+                    initializer_range=0.02)
+
+
+def test_large_c4_shapes_fwd_bwd_against_oracle():
+    """BASELINE config 4 layer shapes (config/uniter-large.json: H=1024, I=4096, 16 heads of 64), two
+    layers deep so the CPU oracle stays in seconds: ragged batch, fwd + bwd, same tolerances as C2."""
+    _require_gpu()
+    b = O.synth_batch(6, 24, 40, seed=77, variable=True, min_txt=4, min_bb=10)
+    m = _build(LARGE_SHAPES, 2048).eval()
+    logits = m(**_kw(b))
+    loss = torch.nn.BCEWithLogitsLoss(pos_weight=torch.tensor([1.8], device=DEV))(
+        logits.squeeze(1), b["labels"].float().to(DEV))
+    loss.backward()
+    ref_logits, ref_loss, sd = _oracle_run(m, LARGE_SHAPES, b)
+    assert (logits.detach().cpu() - ref_logits).abs().max() <= LOGIT_TOL
+    assert abs(loss.item() - ref_loss.item()) <= LOSS_RTOL * abs(ref_loss.item())
+    names = [n for n, p in m.named_parameters() if sd[n].grad is not None and p.grad is not None]
+    got = torch.cat([dict(m.named_parameters())[n].grad.detach().cpu().flatten() for n in names])
+    want = torch.cat([sd[n].grad.flatten() for n in names])
+    assert _cos(got, want) > 0.995
+    for n in ("uniter_model.encoder.layer.1.intermediate.dense.weight",
+              "uniter_model.encoder.layer.0.attention.self.value.weight",
+              "uniter_model.encoder.layer.0.output.LayerNorm.weight",
+              "uniter_model.img_embeddings.img_linear.weight"):
+        assert _cos(dict(m.named_parameters())[n].grad.detach().cpu(), sd[n].grad) > 0.98, n
+
+
+def test_train_step_matches_reference_optimizer_semantics():
+    """SURVEY §8a row 16 (train_template.py:89-109, utils/optim_utils.py:16-46): gradients of the
+    accumulation window are summed, divided by the window length, clipped to max_grad_norm (global L2),
+    then torch.optim.Adam with L2 weight decay on everything whose name has no 'bias' / 'LayerNorm.bias' /
+    'LayerNorm.weight', and zeroed. The fused optimizer (3 launches over the flat buffers) must land on
+    the same parameters as torch.optim.Adam fed the SAME gradients, for two consecutive steps (bias
+    correction, moment state), and must refresh the bf16 weight shadow the GEMMs read."""
+    _require_gpu()
+    from meme_challenge_b200.train import TrainStep, NO_DECAY
+    cfg = dict(TINY)
+    cfg["hidden_dropout_prob"] = 0.0
+    cfg["attention_probs_dropout_prob"] = 0.0
+    m = _build(cfg, IMG_DIM).train()
+    lr, wd, accum, max_norm = 1e-3, 1e-3, 2, 0.01     # max_norm small enough that clipping is active
+    ts = TrainStep(m, lr=lr, weight_decay=wd, gradient_accumulation=accum, max_grad_norm=max_norm, pos_wt=1.8)
+    names = [n for n, _ in m.named_parameters()]
+    ref_p = [p.detach().clone().requires_grad_(True) for _, p in m.named_parameters()]
+    decay = [p for n, p in zip(names, ref_p) if not any(nd in n for nd in NO_DECAY)]
+    no_decay = [p for n, p in zip(names, ref_p) if any(nd in n for nd in NO_DECAY)]
+    assert decay and no_decay
+    opt = torch.optim.Adam([{"params": decay, "weight_decay": wd}, {"params": no_decay, "weight_decay": 0.0}], lr=lr)
+    for step in range(2):
+        batches = []
+        for i in range(accum):
+            b = O.synth_batch(4, 12, 10, seed=40 + 2 * step + i, variable=True, img_dim=IMG_DIM,
+                              vocab=TINY["vocab_size"], min_txt=2, min_bb=2)
+            d = {k: v.to(DEV) for k, v in b.items() if torch.is_tensor(v)}
+            d["labels"] = b["labels"].float().to(DEV)
+            batches.append(d)
+        for i, d in enumerate(batches):
+            ts.micro_step(d, last=(i == accum - 1))
+        grads = [p.grad.detach().clone() for _, p in m.named_parameters()]   # summed over the window
+        ts.optimizer_step()
+        # reference on the same gradients
+        for rp, g in zip(ref_p, grads):
+            rp.grad = g / accum
+        total = torch.nn.utils.clip_grad_norm_(ref_p, max_norm)
+        assert total > max_norm, "pick max_norm so that the clip is exercised"
+        opt.step()
+        assert abs(ts.gnorm.item() - total.item()) <= 1e-4 * total.item()
+        worst = 0.0
+        for (n, p), rp in zip(m.named_parameters(), ref_p):
+            worst = max(worst, (p.detach() - rp.detach()).abs().max().item())
+            assert torch.allclose(p.detach(), rp.detach(), rtol=1e-5, atol=2e-7), (step, n)
+            assert p.grad is None or p.grad.abs().max() == 0, (step, n)       # zero_grad
+        # the bf16 shadow (what the next forward's GEMMs read) follows the fp32 master weights
+        w = m.uniter_model.encoder.layer[0].intermediate.dense.weight
+        assert torch.equal(ts.store.w16(w), w.detach().bfloat16())
+
+
 # ----------------------------------------------------------------------------------------------
 # optimal transport (model/ot.py): golden vectors from the unmodified reference + oracle
 # ----------------------------------------------------------------------------------------------
