@@ -221,6 +221,8 @@ def run_b200(args, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         import datetime
+        if args.nccl_max_ctas > 0:
+            os.environ.setdefault("NCCL_MAX_CTAS", str(args.nccl_max_ctas))
         dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     L = _lib.lib()
 
@@ -234,7 +236,7 @@ def run_b200(args, rank, world, local_rank):
     if world == 1:
         dp_modes = ["eager"] if args.no_graph else ["graph", "eager"]
     ts = TrainStep(model, lr=3e-5, weight_decay=1e-3, gradient_accumulation=ACCUM, max_grad_norm=5.0, pos_wt=1.8,
-                   overlap_comm=True)
+                   overlap_comm=True, comm_sm_reserve=args.comm_sm_reserve if world > 1 else 0)
 
     # synthetic data: a ring of distinct host batches (pinned) and their device copies
     n_sets = 4
@@ -388,6 +390,8 @@ def run_b200(args, rank, world, local_rank):
                 "config": {"workload": WORKLOAD, "global_batch": B * world, "grad_accum": ACCUM,
                            "memes_per_step": ACCUM * B * world, "parallelism": "dp%d" % world,
                            "cuda_graph": use_graph, "dp_mode": dp_mode if world > 1 else None,
+                           "nccl_max_ctas": args.nccl_max_ctas if world > 1 else None,
+                           "comm_sm_reserve": args.comm_sm_reserve if world > 1 else None,
                            "l2": "per-step working set (~0.75 GB saved activations + 1.5 GB fp32 params/grads/Adam "
                                  "state + 0.2 GB bf16 weights) exceeds the 126 MB L2; inputs rotate over %d batch sets" % n_sets,
                            "model_tflop_per_s": round(value * GFLOP_PER_MEME / 1e3, 1),
@@ -421,6 +425,11 @@ def main():
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--dp-mode", default="auto", choices=["auto", "graph-overlap", "graph", "eager"],
                     help="N > 1: how the data-parallel step is launched (auto = first mode that captures)")
+    ap.add_argument("--nccl-max-ctas", type=int, default=16,
+                    help="N > 1: cap NCCL's CTAs per collective (0 = NCCL default). 16 measured best on 2 and 8 B200s: "
+                         "the bucket all-reduces overlap the backward pass and every NCCL CTA owns an SM while it runs")
+    ap.add_argument("--comm-sm-reserve", type=int, default=0,
+                    help="N > 1: SMs left to NCCL while all-reduces overlap the backward pass")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup)
     rank = int(os.environ.get("RANK", "0"))

@@ -39,6 +39,14 @@ long long b200u_launch_count(void);
  * first global-memory access, so its launch + prologue overlap the tail of the preceding kernel
  * on the stream (also inside captured CUDA graphs). 0 turns the attribute off. */
 int b200u_set_pdl(int on);
+/* Size persistent grids (GEMM tile loops, row kernels) for at most n SMs (0 = all). The data-parallel
+ * step sets this while gradient all-reduces run beside the backward pass: NCCL's CTAs own their SMs,
+ * and a 148-CTA persistent grid that cannot be fully resident would run as two waves. */
+int b200u_set_sm_limit(int n);
+/* Backward pass of b200u_bert_layer_bwd: 1 (default) = weight-gradient GEMMs run on a library-owned
+ * side stream forked from / joined to the caller's stream with events (capturable), so they fill the
+ * SMs the critical-path kernels leave idle; 0 = everything on the caller's stream. */
+int b200u_set_bwd_streams(int two_streams);
 /* Event-time every tcgen05 GEMM launch (bench.py roofline leg). enable(n) arms up to n records,
  * collect() synchronises and returns summed duration / algorithmic FLOPs (2MNK) / record count.
  * Must not be armed during CUDA-graph capture. */
@@ -165,11 +173,14 @@ int b200u_pos_linear_wgrad(const void* dp, const float* pos7, float* dW, int n, 
 int b200u_attention_fwd(const void* qkv, const float* mask, void* ctx, float* lse, int B, int L,
                         int num_heads, int H, const b200u_dropout_t* drop, b200u_stream_t stream);
 /* scratch: caller-owned device buffer of b200u_attention_bwd_scratch_bytes(B, L, heads) bytes
- * (bf16 probabilities and score gradients handed from the dQ launch to the dK/dV launch). */
+ * (bf16 probabilities and score gradients handed from the dQ launch to the dK/dV launch; only
+ * touched when L > 176, shorter sequences run the fused single-kernel backward).
+ * dbias_qkv (f32 [3H], may be NULL): += column sums of the bf16 dqkv, i.e. the bias gradient of the
+ * fused QKV projection (model/layer.py:64-66), accumulated inside the same launch. */
 size_t b200u_attention_bwd_scratch_bytes(int B, int L, int num_heads);
 int b200u_attention_bwd(const void* qkv, const float* mask, const void* ctx, const void* dctx,
-                        const float* lse, void* dqkv, void* scratch, int B, int L, int num_heads,
-                        int H, const b200u_dropout_t* drop, b200u_stream_t stream);
+                        const float* lse, void* dqkv, void* scratch, float* dbias_qkv, int B, int L,
+                        int num_heads, int H, const b200u_dropout_t* drop, b200u_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * BertLayer.forward / its backward as one call each (model/layer.py:159-170). Weight matrices

@@ -19,6 +19,8 @@ SIGNATURES = {
     "b200u_device_info": (_i, [C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
     "b200u_launch_count": (_ll, []),
     "b200u_set_pdl": (_i, [_i]),
+    "b200u_set_sm_limit": (_i, [_i]),
+    "b200u_set_bwd_streams": (_i, [_i]),
     "b200u_prof_enable": (_i, [_i]),
     "b200u_prof_collect": (_i, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_i)]),
     "b200u_gemm": (_i, [_p, _p]),
@@ -36,7 +38,7 @@ SIGNATURES = {
     "b200u_pos_linear_wgrad": (_i, [_p, _p, _p, _i, _i, _p]),
     "b200u_attention_fwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p, _p]),
     "b200u_attention_bwd_scratch_bytes": (_sz, [_i, _i, _i]),
-    "b200u_attention_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p]),
+    "b200u_attention_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p]),
     "b200u_bert_layer_fwd": (_i, [_p, _p, _p, _p, _p]),
     "b200u_bert_layer_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p]),
     "b200u_pooler_fwd": (_i, [_p, _ll, _p, _p, _p, _i, _i, _p]),

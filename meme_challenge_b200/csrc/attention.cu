@@ -505,13 +505,31 @@ attn_bwd_dkv_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dctx,
 //   phase 1 (warp = 16 query rows): S, dPd in 32-key chunks -> Pd, dS tiles in smem ; dQ = dS·K
 //   phase 2 (warp = 16 key rows)  : dV = Pdᵀ·dO ; dK = dSᵀ·Q  (ldmatrix.trans over the smem tiles)
 // ---------------------------------------------------------------------------------------
+// Column sums (over this warp's 16 rows) of a 16x64 accumulator tile, taken on the bf16-rounded
+// values the stores write; lanes 0-3 end up with the sums of columns nt*8 + 2*lane + {0,1}.
+__device__ __forceinline__ void frag_colsum(const float (&a)[8][4], float (&c)[8][2]) {
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+        float2 lo = unpack_bf16(pack_bf16(a[nt][0], a[nt][1]));
+        float2 hi = unpack_bf16(pack_bf16(a[nt][2], a[nt][3]));
+        float x = lo.x + hi.x, y = lo.y + hi.y;
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) {
+            x += __shfl_xor_sync(0xffffffffu, x, o);
+            y += __shfl_xor_sync(0xffffffffu, y, o);
+        }
+        c[nt][0] = x;
+        c[nt][1] = y;
+    }
+}
+
 constexpr int FUSED_MAX_LP = 176;
 
 __global__ void __launch_bounds__(FUSED_MAX_LP * 2, 1)
 attn_bwd_fused_kernel(const bf16* __restrict__ qkv, const float* __restrict__ mask,
                       const bf16* __restrict__ ctx, const bf16* __restrict__ dctx,
-                      const float* __restrict__ lse, bf16* __restrict__ dqkv, int L, int LP, int nh,
-                      int H, DropoutCfg drop) {
+                      const float* __restrict__ lse, bf16* __restrict__ dqkv,
+                      float* __restrict__ dbias, int L, int LP, int nh, int H, DropoutCfg drop) {
     pdl_sync();
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const int TILE = LP * HD;  // elements of one [LP][64] tile
@@ -648,7 +666,17 @@ attn_bwd_fused_kernel(const bf16* __restrict__ qkv, const float* __restrict__ ma
         if (v0) *reinterpret_cast<uint32_t*>(dbase + (size_t)x0 * ld + nt * 8 + t2) = pack_bf16(dq[nt][0], dq[nt][1]);
         if (v1) *reinterpret_cast<uint32_t*>(dbase + (size_t)x1 * ld + nt * 8 + t2) = pack_bf16(dq[nt][2], dq[nt][3]);
     }
-    __syncthreads();  // every warp's rows of Pd / dS are in shared memory
+    float cq[8][2];
+    if (dbias) frag_colsum(dq, cq);
+    __syncthreads();  // every warp's rows of Pd / dS are in shared memory (and K / V are dead)
+    float* sCol = reinterpret_cast<float*>(sK);  // [warps][3][64] partial bias-gradient column sums
+    if (dbias && lane < 4) {
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            sCol[(warp * 3 + 0) * 64 + nt * 8 + t2] = cq[nt][0];
+            sCol[(warp * 3 + 0) * 64 + nt * 8 + t2 + 1] = cq[nt][1];
+        }
+    }
 
     // ---------------- phase 2: this warp's 16 key rows, reduction over all queries ----------------
     float dk[8][4], dv[8][4];
@@ -673,6 +701,27 @@ attn_bwd_fused_kernel(const bf16* __restrict__ qkv, const float* __restrict__ ma
         if (v1) {
             *reinterpret_cast<uint32_t*>(dbase + (size_t)x1 * ld + H + nt * 8 + t2) = pack_bf16(dk[nt][2], dk[nt][3]);
             *reinterpret_cast<uint32_t*>(dbase + (size_t)x1 * ld + 2 * H + nt * 8 + t2) = pack_bf16(dv[nt][2], dv[nt][3]);
+        }
+    }
+    if (dbias) {
+        float ck[8][2], cv[8][2];
+        frag_colsum(dk, ck);
+        frag_colsum(dv, cv);
+        if (lane < 4) {
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                sCol[(warp * 3 + 1) * 64 + nt * 8 + t2] = ck[nt][0];
+                sCol[(warp * 3 + 1) * 64 + nt * 8 + t2 + 1] = ck[nt][1];
+                sCol[(warp * 3 + 2) * 64 + nt * 8 + t2] = cv[nt][0];
+                sCol[(warp * 3 + 2) * 64 + nt * 8 + t2 + 1] = cv[nt][1];
+            }
+        }
+        __syncthreads();
+        const int nw = nthreads >> 5;
+        for (int c = tid; c < 192; c += nthreads) {  // (matrix, column) = (c / 64, c % 64)
+            float acc = 0.f;
+            for (int w = 0; w < nw; ++w) acc += sCol[w * 192 + c];
+            atomicAdd(dbias + (c >> 6) * H + h * HD + (c & 63), acc);
         }
     }
 }
@@ -702,7 +751,7 @@ static int launch_fwd(const void* qkv, const float* mask, void* ctx, float* lse,
 }
 
 static int launch_bwd(const void* qkv, const float* mask, const void* ctx, const void* dctx,
-                      const float* lse, void* dqkv, void* scratch, int B, int L, int nh, int H,
+                      const float* lse, void* dqkv, void* scratch, float* dbias, int B, int L, int nh, int H,
                       DropoutCfg dc, cudaStream_t stream) {
     const int LP = (L + 15) / 16 * 16;
     bf16* scrP = (bf16*)scratch;
@@ -726,7 +775,7 @@ static int launch_bwd(const void* qkv, const float* mask, const void* ctx, const
             B200U_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             set3 = smem;
         }
-        launch_k(attn_bwd_fused_kernel, dim3(B * nh), dim3(LP * 2), smem, stream, (const bf16*)qkv, mask, (const bf16*)ctx, (const bf16*)dctx, lse, (bf16*)dqkv, L, LP, nh, H, dc);
+        launch_k(attn_bwd_fused_kernel, dim3(B * nh), dim3(LP * 2), smem, stream, (const bf16*)qkv, mask, (const bf16*)ctx, (const bf16*)dctx, lse, (bf16*)dqkv, dbias, L, LP, nh, H, dc);
         B200U_CHECK_LAUNCH("attn_bwd_fused_kernel");
         return B200U_OK;
     }
@@ -735,6 +784,7 @@ static int launch_bwd(const void* qkv, const float* mask, const void* ctx, const
     B200U_CHECK_LAUNCH("attn_bwd_dq_kernel");
     launch_k(attn_bwd_dkv_kernel, dim3(grid), dim3(128), smem2, stream, (const bf16*)qkv, (const bf16*)dctx, scrP, scrS, (bf16*)dqkv, L, LP, nh, H);
     B200U_CHECK_LAUNCH("attn_bwd_dkv_kernel");
+    if (dbias) return b200u_colsum_accum(dqkv, 3 * H, dbias, B * L, 3 * H, stream);
     return B200U_OK;
 }
 
@@ -761,9 +811,9 @@ extern "C" size_t b200u_attention_bwd_scratch_bytes(int B, int L, int num_heads)
 }
 
 extern "C" int b200u_attention_bwd(const void* qkv, const float* mask, const void* ctx,
-                                   const void* dctx, const float* lse, void* dqkv, void* scratch, int B,
-                                   int L, int num_heads, int H, const b200u_dropout_t* drop,
-                                   b200u_stream_t stream_) {
+                                   const void* dctx, const float* lse, void* dqkv, void* scratch,
+                                   float* dbias_qkv, int B, int L, int num_heads, int H,
+                                   const b200u_dropout_t* drop, b200u_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     B200U_CHECK_ARG(qkv && mask && ctx && dctx && lse && dqkv && scratch, "attention_bwd: null pointer");
     B200U_CHECK_ARG(num_heads > 0 && H == num_heads * HD, "attention_bwd: head dim must be 64 (H=%d heads=%d)", H, num_heads);
@@ -771,5 +821,5 @@ extern "C" int b200u_attention_bwd(const void* qkv, const float* mask, const voi
     if (B == 0) return B200U_OK;
     DropoutCfg dc = make_drop(drop);
     B200U_CHECK_ARG(dc.thresh16 == 0 || dc.seed_ptr, "attention_bwd: dropout needs seed_ptr");
-    return launch_bwd(qkv, mask, ctx, dctx, lse, dqkv, scratch, B, L, num_heads, H, dc, stream);
+    return launch_bwd(qkv, mask, ctx, dctx, lse, dqkv, scratch, dbias_qkv, B, L, num_heads, H, dc, stream);
 }

@@ -8,11 +8,14 @@
 //   y1  = dropout(ctx·Woᵀ + bo) + x0 ; x1 = LN1(y1)      layer.py:111-115
 //   u   = x1·W1ᵀ + b1 ; g = gelu(u)                      layer.py:139-142
 //   y2  = dropout(g·W2ᵀ + b2) + x1 ; x2 = LN2(y2)        layer.py:152-156
-// backward (11 launches): the exact transposes, weight grads accumulated in fp32 (+=).
+// backward (12 launches): the exact transposes, weight grads accumulated in fp32 (+=).
 #include "../../include/b200u.h"
 #include "common.cuh"
 
+#include <stdlib.h>
 #include <string.h>
+
+#include <mutex>
 
 using namespace b200u;
 
@@ -78,6 +81,55 @@ extern "C" int b200u_bert_layer_fwd(const b200u_layer_params_t* p, const void* x
     return B200U_OK;
 }
 
+// ---- side stream for the weight-gradient GEMMs of the backward pass -------------------------------
+// dW GEMMs (and the b1 bias-gradient column sum) are off the critical path: nothing in the layer's
+// backward chain consumes them. They run on a library-owned side stream, forked from / joined to the
+// caller's stream with events (capturable: the side stream joins the capture through the fork event),
+// so their CTAs fill the SMs that the critical-path kernels leave idle -- partial second waves of the
+// persistent GEMMs (252 tiles on 148 SMs), the 126-CTA N=768 GEMMs, the 192-CTA attention backward.
+namespace {
+
+struct SideCtx {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t fork[4] = {nullptr, nullptr, nullptr, nullptr};  // main -> side: producer of each side job is done
+    cudaEvent_t w2_done = nullptr;                               // side -> main: dz may be overwritten
+    cudaEvent_t all_done = nullptr;                              // side -> main: join at the end of the layer
+    bool ok = false;
+};
+// b200u_set_bwd_streams(): 1 = weight gradients on the side stream, 0 = single stream
+// (the environment variable B200U_BWD_STREAMS=0 selects the single-stream order at load time)
+int g_side_mode = [] {
+    const char* e = getenv("B200U_BWD_STREAMS");
+    return (e && e[0] == '0') ? 0 : 1;
+}();
+
+SideCtx* side_ctx() {
+    // one context per device, shared by all host threads (PyTorch runs backward on its own thread;
+    // calls for one device are serialised by the caller's stream order)
+    static SideCtx ctx[16];
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+    SideCtx& c = ctx[dev];
+    if (!c.ok) {
+        if (cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        for (int i = 0; i < 4; ++i)
+            if (cudaEventCreateWithFlags(&c.fork[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&c.w2_done, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&c.all_done, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        c.ok = true;
+    }
+    return &c;
+}
+
+}  // namespace
+
+extern "C" int b200u_set_bwd_streams(int two_streams) {
+    g_side_mode = two_streams ? 1 : 0;
+    return B200U_OK;
+}
+
 extern "C" int b200u_bert_layer_bwd(const b200u_layer_params_t* p, const void* x0,
                                     const b200u_layer_saved_t* s, const void* dx2,
                                     const b200u_layer_grads_t* g, const b200u_layer_scratch_t* w,
@@ -91,39 +143,62 @@ extern "C" int b200u_bert_layer_bwd(const b200u_layer_params_t* p, const void* x
     const b200u_dropout_t d_h2 = site(p, SITE_HID2, p->p_hidden);
     const int impl = p->gemm_impl;
 
+    SideCtx* sc = g_side_mode ? side_ctx() : nullptr;
+    cudaStream_t sd = sc ? sc->stream : st;  // where the weight-gradient work goes
+    // fork k: the side stream may start job k once everything enqueued on `st` so far is done
+#define FORK(k)                                                     \
+    do {                                                            \
+        if (sc) {                                                   \
+            B200U_CHECK_CUDA(cudaEventRecord(sc->fork[k], st));     \
+            B200U_CHECK_CUDA(cudaStreamWaitEvent(sd, sc->fork[k], 0)); \
+        }                                                           \
+    } while (0)
+
     // LN2 backward: dres (= grad of x1 through the residual) and dz2 (= grad of the FFN2 output)
     void* dz2 = p->p_hidden > 0.f ? w->dz : w->dres;
     TRY(b200u_layernorm_bwd(dx2, s->y2, B200U_BF16, s->mean2, s->rstd2, p->ln2_g, w->dres,
                             p->p_hidden > 0.f ? w->dz : nullptr, g->dln2_g, g->dln2_b, g->db2, M, H, &d_h2,
                             0, st));
-    // FFN2: dW2[H,I] += dz2ᵀ·g ; du = (dz2·W2) * gelu'(u)
+    // FFN2: dW2[H,I] += dz2ᵀ·g (side) ; du = (dz2·W2) * gelu'(u)
+    FORK(0);
     TRY(gemm(H, I, M, dz2, H, 1, s->g, I, 1, B200U_EPI_ATOMIC_F32, g->dW2, I, nullptr, 0, nullptr, nullptr,
-             0, nullptr, impl, st));
+             0, nullptr, impl, sd));
+    if (sc) B200U_CHECK_CUDA(cudaEventRecord(sc->w2_done, sd));
     TRY(gemm(M, I, H, dz2, H, 0, p->W2, I, 1, B200U_EPI_DGELU, w->du, I, nullptr, 0, nullptr, s->u, I,
              nullptr, impl, st));
-    TRY(b200u_colsum_accum(w->du, I, g->db1, M, I, st));
-    // FFN1: dW1[I,H] += duᵀ·x1 ; dx1 = du·W1 + dres
+    // FFN1: db1 += colsum(du), dW1[I,H] += duᵀ·x1 (side) ; dx1 = du·W1 + dres
+    FORK(1);
+    TRY(b200u_colsum_accum(w->du, I, g->db1, M, I, sd));
     TRY(gemm(I, H, M, w->du, I, 1, s->x1, H, 1, B200U_EPI_ATOMIC_F32, g->dW1, H, nullptr, 0, nullptr,
-             nullptr, 0, nullptr, impl, st));
+             nullptr, 0, nullptr, impl, sd));
     TRY(gemm(M, H, I, w->du, I, 0, p->W1, H, 1, B200U_EPI_ADD, w->dx1, H, nullptr, 0, nullptr, w->dres, H,
              nullptr, impl, st));
-    // LN1 backward
+    // LN1 backward (rewrites dres / dz: the FFN2 weight gradient must have consumed dz2 first)
+    if (sc) B200U_CHECK_CUDA(cudaStreamWaitEvent(st, sc->w2_done, 0));
     void* dz1 = p->p_hidden > 0.f ? w->dz : w->dres;
     TRY(b200u_layernorm_bwd(w->dx1, s->y1, B200U_BF16, s->mean1, s->rstd1, p->ln1_g, w->dres,
                             p->p_hidden > 0.f ? w->dz : nullptr, g->dln1_g, g->dln1_b, g->dbo, M, H, &d_h1,
                             0, st));
-    // attention output projection: dWo[H,H] += dz1ᵀ·ctx ; dctx = dz1·Wo
+    // attention output projection: dWo[H,H] += dz1ᵀ·ctx (side) ; dctx = dz1·Wo
+    FORK(2);
     TRY(gemm(H, H, M, dz1, H, 1, s->ctx, H, 1, B200U_EPI_ATOMIC_F32, g->dWo, H, nullptr, 0, nullptr,
-             nullptr, 0, nullptr, impl, st));
+             nullptr, 0, nullptr, impl, sd));
     TRY(gemm(M, H, H, dz1, H, 0, p->Wo, H, 1, B200U_EPI_STORE, w->dctx, H, nullptr, 0, nullptr, nullptr, 0,
              nullptr, impl, st));
-    TRY(b200u_attention_bwd(s->qkv, p->mask, s->ctx, w->dctx, s->lse, w->dqkv, w->attn, p->B, p->L, p->heads, H,
-                            &d_attn, st));
-    TRY(b200u_colsum_accum(w->dqkv, 3 * H, g->dbqkv, M, 3 * H, st));
-    // QKV projection: dWqkv[3H,H] += dqkvᵀ·x0 ; dx0 = dqkv·Wqkv + dres
+    // (the QKV bias gradient, column sums of dqkv, is accumulated inside the attention backward)
+    TRY(b200u_attention_bwd(s->qkv, p->mask, s->ctx, w->dctx, s->lse, w->dqkv, w->attn, g->dbqkv, p->B, p->L,
+                            p->heads, H, &d_attn, st));
+    // QKV projection: dWqkv[3H,H] += dqkvᵀ·x0 (side) ; dx0 = dqkv·Wqkv + dres
+    FORK(3);
     TRY(gemm(3 * H, H, M, w->dqkv, 3 * H, 1, x0, H, 1, B200U_EPI_ATOMIC_F32, g->dWqkv, H, nullptr, 0,
-             nullptr, nullptr, 0, nullptr, impl, st));
+             nullptr, nullptr, 0, nullptr, impl, sd));
     TRY(gemm(M, H, 3 * H, w->dqkv, 3 * H, 0, p->Wqkv, H, 1, B200U_EPI_ADD, dx0, H, nullptr, 0, nullptr,
              w->dres, H, nullptr, impl, st));
+    if (sc) {
+        // join: the scratch buffers the side jobs read (dz, du, dqkv) are rewritten by the next layer
+        B200U_CHECK_CUDA(cudaEventRecord(sc->all_done, sd));
+        B200U_CHECK_CUDA(cudaStreamWaitEvent(st, sc->all_done, 0));
+    }
+#undef FORK
     return B200U_OK;
 }

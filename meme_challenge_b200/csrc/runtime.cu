@@ -37,6 +37,9 @@ static int g_pdl = 1;
 bool pdl_enabled() { return g_pdl != 0; }
 void set_pdl(int on) { g_pdl = on; }
 
+static int g_sm_limit = 0;  // b200u_set_sm_limit(): persistent grids are sized to at most this many SMs
+void set_sm_limit(int n) { g_sm_limit = n; }
+
 int num_sms() {
     static int cached = 0;
     if (!cached) {
@@ -47,7 +50,7 @@ int num_sms() {
         else
             return 148;
     }
-    return cached;
+    return (g_sm_limit > 0 && g_sm_limit < cached) ? g_sm_limit : cached;
 }
 
 }  // namespace b200u
@@ -55,6 +58,11 @@ int num_sms() {
 extern "C" const char* b200u_last_error_string(void) { return b200u::g_err; }
 
 extern "C" int b200u_version(void) { return 100; }
+
+extern "C" int b200u_set_sm_limit(int n) {
+    b200u::set_sm_limit(n);
+    return B200U_OK;
+}
 
 extern "C" int b200u_set_pdl(int on) {
     b200u::set_pdl(on);

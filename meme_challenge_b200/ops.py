@@ -136,12 +136,15 @@ def attention_fwd(qkv, mask, B, L, heads, H, drop=None, want_lse=True):
     return ctx, lse
 
 
-def attention_bwd(qkv, mask, ctx, dctx, lse, B, L, heads, H, drop=None):
+def attention_bwd(qkv, mask, ctx, dctx, lse, B, L, heads, H, drop=None, dbias_qkv=None):
+    """dqkv of the fused attention; dbias_qkv (f32 [3H], optional) += column sums of dqkv."""
     dqkv = torch.empty_like(qkv)
     nbytes = _lib.lib().b200u_attention_bwd_scratch_bytes(B, L, heads)
     scratch = torch.empty(nbytes, device=qkv.device, dtype=torch.uint8)
-    _call("b200u_attention_bwd", P(qkv), P(mask), P(ctx), P(dctx), P(lse), P(dqkv), P(scratch), B, L, heads, H,
-          _drop_ref(drop))
+    if dbias_qkv is not None:
+        assert dbias_qkv.dtype == torch.float32 and dbias_qkv.numel() == 3 * H and dbias_qkv.is_contiguous()
+    _call("b200u_attention_bwd", P(qkv), P(mask), P(ctx), P(dctx), P(lse), P(dqkv), P(scratch), P(dbias_qkv),
+          B, L, heads, H, _drop_ref(drop))
     return dqkv
 
 

@@ -82,7 +82,7 @@ class GradBuckets(object):
 class TrainStep(object):
     def __init__(self, model, lr=3e-5, weight_decay=1e-3, betas=(0.9, 0.999), eps=1e-8,
                  gradient_accumulation=2, max_grad_norm=5.0, pos_wt=1.8, process_group=None,
-                 overlap_comm=True):
+                 overlap_comm=True, comm_sm_reserve=0):
         self.model = model
         self.um = model.uniter_model
         self.accum = int(gradient_accumulation)
@@ -94,6 +94,9 @@ class TrainStep(object):
         if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
             self.world = torch.distributed.get_world_size(process_group)
         self.overlap_comm = overlap_comm
+        # SMs left to NCCL while bucket all-reduces overlap the last micro-batch's backward: the
+        # persistent kernels of that backward are sized for (SM count - reserve) so they stay one wave
+        self.comm_sm_reserve = int(comm_sm_reserve)
 
         # one flat store for the whole MemeUniter (UNITER + classification head)
         store = FlatStore(model)
@@ -157,7 +160,16 @@ class TrainStep(object):
         self.um._layer_grad_ready_cb = self._on_layer_done if (comm and self.overlap_comm) else None
         logits = self.model(**kw)
         loss, dlogits, probs = F_.bce_with_logits(logits, batch["labels"], self.pos_wt)
-        torch.autograd.backward(logits, dlogits.view_as(logits))
+        limit = comm and self.overlap_comm and self.comm_sm_reserve > 0
+        if limit:
+            sms = C.c_int()
+            _lib.check(_lib.lib().b200u_device_info(C.byref(sms), None, None))
+            _lib.lib().b200u_set_sm_limit(max(1, sms.value - self.comm_sm_reserve))
+        try:
+            torch.autograd.backward(logits, dlogits.view_as(logits))
+        finally:
+            if limit:
+                _lib.lib().b200u_set_sm_limit(0)
         self.um._layer_grad_ready_cb = None
         if comm:
             if not self.overlap_comm:

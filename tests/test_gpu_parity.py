@@ -178,8 +178,13 @@ def test_attention_fwd_bwd(L, heads):
 
     ctx, lse = ops.attention_fwd(qkv.to(DEV), mask_add.to(DEV), B, L, heads, H)
     assert (ctx.float().cpu() - ctx_ref.detach()).abs().max() < 2e-2
-    dqkv = ops.attention_bwd(qkv.to(DEV), mask_add.to(DEV), ctx, dctx.to(DEV), lse, B, L, heads, H)
+    dbias = torch.full((3 * H,), 0.5, device=DEV)   # accumulated into (+=), not overwritten
+    dqkv = ops.attention_bwd(qkv.to(DEV), mask_add.to(DEV), ctx, dctx.to(DEV), lse, B, L, heads, H,
+                             dbias_qkv=dbias)
     g = dqkv.float().cpu()
+    # fused QKV bias gradient = column sums of the bf16 dqkv the same launch wrote
+    want_db = dqkv.float().sum(0).cpu() + 0.5
+    assert (dbias.cpu() - want_db).abs().max() <= 1e-3 * max(1.0, want_db.abs().max().item())
     assert _cos(g, x.grad) > 0.999
     assert (g - x.grad).abs().max() < 3e-2 * x.grad.abs().max()
     # masked keys receive exactly zero dK / dV, like the reference (exp underflow)
