@@ -366,7 +366,10 @@ def run_b200(args, rank, world, local_rank):
         tms, tfl, nlaunch, detail = _gemm_roofline(dev)
         ach = tfl / (tms * 1e-3) / 1e12
         roof = {"bound": "tensor", "achieved": round(ach, 1), "peak": sus, "unit": "TFLOP/s",
-                "frac": round(ach / sus, 4), "traffic": None,
+                "frac": round(ach / sus, 4),
+                # DRAM bytes per launch (dram__bytes_read + write, ncu --set full, profiles/r01_gemm_ncu_final.txt),
+                # mean over the six captured shapes: reads equal the operand (+ side-input) sizes, i.e. no re-reads
+                "traffic": 17.5e6,
                 "kernel": "gemm_tc_kernel (tcgen05+TMA bf16 GEMM family): %d launches per optimizer step, each shape "
                           "timed as 20 back-to-back launches in a CUDA graph; achieved = sum(2MNK) / sum(duration); "
                           "peak = sustained cuBLAS bf16 (%s)" % (nlaunch, how),

@@ -47,26 +47,43 @@ pooler_bwd_kernel(const float* __restrict__ dpooled, const float* __restrict__ p
     const int nwb = (H + 7) / 8;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if ((int)blockIdx.x < nwb) {
+        // one warp per output row n of dW: lane b keeps dpre[b, n] (32 samples at a time) and the
+        // sample loop broadcasts it with a shuffle, so the h rows stream without dependent loads
         const int n = blockIdx.x * 8 + warp;
         if (n >= H) return;
         float bsum = 0.f;
-        for (int k0 = lane * 4; k0 < H; k0 += 128) {
-            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-            for (int b = 0; b < B; ++b) {
-                const float p = pooled[(size_t)b * H + n];
-                const float dpre = dpooled[(size_t)b * H + n] * (1.0f - p * p);
-                const bf16* hr = h + (size_t)b * row_stride + k0;
-                uint2 u = *reinterpret_cast<const uint2*>(hr);
-                float2 f0 = unpack_bf16(u.x), f1 = unpack_bf16(u.y);
-                a0 = fmaf(dpre, f0.x, a0); a1 = fmaf(dpre, f0.y, a1);
-                a2 = fmaf(dpre, f1.x, a2); a3 = fmaf(dpre, f1.y, a3);
-                if (k0 == 0) bsum += dpre;
+        for (int b0 = 0; b0 < B; b0 += 32) {
+            const int bl = b0 + lane;
+            float mine = 0.f;
+            if (bl < B) {
+                const float p = pooled[(size_t)bl * H + n];
+                mine = dpooled[(size_t)bl * H + n] * (1.0f - p * p);
             }
-            float4* dst = reinterpret_cast<float4*>(dW + (size_t)n * H + k0);
-            float4 cur = *dst;
-            cur.x += a0; cur.y += a1; cur.z += a2; cur.w += a3;
-            *dst = cur;
+            bsum += mine;
+            const int nb = min(32, B - b0);
+            for (int kk = 0; kk < H; kk += 128) {  // warp-uniform trip count (the shuffles need all lanes)
+                const int k0 = kk + lane * 4;
+                const bool on = k0 < H;
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 4
+                for (int b = 0; b < nb; ++b) {
+                    const float dpre = __shfl_sync(0xffffffffu, mine, b);
+                    if (on) {
+                        uint2 u = *reinterpret_cast<const uint2*>(h + (size_t)(b0 + b) * row_stride + k0);
+                        float2 f0 = unpack_bf16(u.x), f1 = unpack_bf16(u.y);
+                        a0 = fmaf(dpre, f0.x, a0); a1 = fmaf(dpre, f0.y, a1);
+                        a2 = fmaf(dpre, f1.x, a2); a3 = fmaf(dpre, f1.y, a3);
+                    }
+                }
+                if (on) {
+                    float4* dst = reinterpret_cast<float4*>(dW + (size_t)n * H + k0);
+                    float4 cur = *dst;
+                    cur.x += a0; cur.y += a1; cur.z += a2; cur.w += a3;
+                    *dst = cur;
+                }
+            }
         }
+        bsum = warp_sum(bsum);
         if (lane == 0 && db) db[n] += bsum;
     } else {
         // one block per (sample, 64-column slice): 4 groups of 64 threads stride over n, then reduce

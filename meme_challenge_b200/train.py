@@ -13,6 +13,7 @@ of nn.DataParallel's per-step parameter broadcast + gradient reduce, train_templ
 """
 import ctypes as C
 import math
+import os
 
 import torch
 
@@ -97,6 +98,9 @@ class TrainStep(object):
         # SMs left to NCCL while bucket all-reduces overlap the last micro-batch's backward: the
         # persistent kernels of that backward are sized for (SM count - reserve) so they stay one wave
         self.comm_sm_reserve = int(comm_sm_reserve)
+        # software-pipeline the micro-batches of a window over two streams (see step()); B200U_PIPELINE=0 disables
+        self.pipeline = os.environ.get("B200U_PIPELINE", "1") != "0"
+        self._aux_stream = None
 
         # one flat store for the whole MemeUniter (UNITER + classification head)
         store = FlatStore(model)
@@ -151,15 +155,25 @@ class TrainStep(object):
         self.comm.reduce_bucket(layer_idx + 1)
 
     # ------------------------------------------------------------------ one micro-batch
-    def micro_step(self, batch, last):
+    def _forward_loss(self, batch, last):
+        """Forward + loss of one micro-batch on the current stream. Returns the state `_backward` needs."""
         kw = dict(input_ids=batch["input_ids"], position_ids=batch["position_ids"],
                   img_feat=batch["img_feat"], img_pos_feat=batch["img_pos_feat"],
                   attention_mask=batch["attn_mask"], gather_index=batch["gather_index"],
                   output_all_encoded_layers=False)
         comm = self.world > 1 and last
+        # the layer hooks are registered during the forward (they capture the callback), so it is only
+        # set around this call
         self.um._layer_grad_ready_cb = self._on_layer_done if (comm and self.overlap_comm) else None
-        logits = self.model(**kw)
+        try:
+            logits = self.model(**kw)
+        finally:
+            self.um._layer_grad_ready_cb = None
         loss, dlogits, probs = F_.bce_with_logits(logits, batch["labels"], self.pos_wt)
+        return logits, dlogits, loss, probs, comm
+
+    def _backward(self, state):
+        logits, dlogits, loss, probs, comm = state
         limit = comm and self.overlap_comm and self.comm_sm_reserve > 0
         if limit:
             sms = C.c_int()
@@ -170,13 +184,15 @@ class TrainStep(object):
         finally:
             if limit:
                 _lib.lib().b200u_set_sm_limit(0)
-        self.um._layer_grad_ready_cb = None
         if comm:
             if not self.overlap_comm:
                 for i in range(len(self.buckets) - 1, 0, -1):
                     self._allreduce_bucket(i)
             self._allreduce_bucket(0)
         return loss, probs
+
+    def micro_step(self, batch, last):
+        return self._backward(self._forward_loss(batch, last))
 
     # ------------------------------------------------------------------ optimizer
     def optimizer_step(self):
@@ -198,11 +214,48 @@ class TrainStep(object):
     # ------------------------------------------------------------------ public: one optimizer step
     def step(self, batches):
         """batches: list of `gradient_accumulation` device batch dicts. Returns the list of
-        (loss[1], probs[B]) device tensors of the micro-batches."""
+        (loss[1], probs[B]) device tensors of the micro-batches.
+
+        The micro-batches of one accumulation window are independent until their gradients meet in the
+        flat buffer, so the window is software-pipelined over two streams: the forward of micro-batch
+        i+1 runs beside the backward of micro-batch i (forward chains and backward chains each leave
+        SMs idle in their launch / first-load / epilogue-drain phases; two chains fill each other's
+        gaps). Backward passes stay ordered (they share scratch buffers and, with world_size > 1, the
+        last one triggers the bucket all-reduces), forwards stay ordered (dropout seed sequence)."""
         assert len(batches) == self.accum
-        outs = []
-        for i, b in enumerate(batches):
-            outs.append(self.micro_step(b, last=(i == len(batches) - 1)))
+        n = len(batches)
+        if n == 1 or not self.pipeline:
+            outs = [self.micro_step(b, last=(i == n - 1)) for i, b in enumerate(batches)]
+        else:
+            main = torch.cuda.current_stream()
+            if self._aux_stream is None:
+                self._aux_stream = torch.cuda.Stream()
+            streams = [main, self._aux_stream]
+            state, outs = {}, [None] * n
+
+            def fwd(i, after):
+                s = streams[i % 2]
+                if after is not None:
+                    s.wait_event(after)
+                with torch.cuda.stream(s):
+                    state[i] = self._forward_loss(batches[i], last=(i == n - 1))
+                    return s.record_event()
+
+            def bwd(i, after):
+                s = streams[i % 2]
+                if after is not None:
+                    s.wait_event(after)
+                with torch.cuda.stream(s):
+                    outs[i] = self._backward(state.pop(i))
+                    return s.record_event()
+
+            ev_f = fwd(0, None)
+            ev_b = None
+            for i in range(n):
+                ev_next = fwd(i + 1, ev_f) if i + 1 < n else None
+                ev_b = bwd(i, ev_b)
+                ev_f = ev_next
+            main.wait_event(ev_b)     # join before the optimizer (and before the caller reads the outputs)
         self.optimizer_step()
         self.host_step += 1
         return outs

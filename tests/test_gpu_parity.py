@@ -473,6 +473,62 @@ def test_train_step_matches_reference_optimizer_semantics():
         assert torch.equal(ts.store.w16(w), w.detach().bfloat16())
 
 
+def test_pipelined_window_equals_sequential_window():
+    """TrainStep.step software-pipelines the micro-batches of an accumulation window over two streams
+    (forward i+1 beside backward i) and runs the weight-gradient GEMMs on a side stream: the parameters
+    after two optimizer steps must equal those of the plain sequential, single-stream order (fp32
+    accumulation order is the only difference), eagerly and through CUDA-graph replay."""
+    _require_gpu()
+    from meme_challenge_b200 import _lib
+    from meme_challenge_b200.train import TrainStep
+    cfg = dict(TINY)
+    cfg["hidden_dropout_prob"] = 0.0
+    cfg["attention_probs_dropout_prob"] = 0.0
+
+    def batches(step):
+        out = []
+        for i in range(2):
+            b = O.synth_batch(4, 12, 10, seed=60 + 2 * step + i, img_dim=IMG_DIM, vocab=TINY["vocab_size"],
+                              min_txt=2, min_bb=2)
+            d = {k: v.to(DEV) for k, v in b.items() if torch.is_tensor(v)}
+            d["labels"] = b["labels"].float().to(DEV)
+            out.append(d)
+        return out
+
+    def run(pipeline, graph):
+        _lib.lib().b200u_set_bwd_streams(1 if pipeline else 0)
+        try:
+            m = _build(cfg, IMG_DIM, seed=3).train()
+            ts = TrainStep(m, lr=1e-3, weight_decay=1e-3, gradient_accumulation=2, max_grad_norm=5.0, pos_wt=1.8)
+            ts.pipeline = pipeline
+            losses = []
+            if graph:
+                ts.capture(batches(0), warmup=0)
+                for step in range(2):
+                    ts.load_static(batches(step))
+                    outs = ts.replay()
+                    losses.append([float(o[0].item()) for o in outs])
+            else:
+                for step in range(2):
+                    outs = ts.step(batches(step))
+                    losses.append([float(o[0].item()) for o in outs])
+            torch.cuda.synchronize()
+            return {n: p.detach().clone() for n, p in m.named_parameters()}, losses
+        finally:
+            _lib.lib().b200u_set_bwd_streams(1)
+
+    ref_p, ref_l = run(False, False)
+    for graph in (False, True):
+        got_p, got_l = run(True, graph)
+        assert np.allclose(np.array(got_l), np.array(ref_l), rtol=1e-5, atol=1e-6), (graph, got_l, ref_l)
+        for n in ref_p:
+            # Adam's first steps move every weight by ~lr regardless of gradient size, so a gradient
+            # that differs in the last fp32 bits can move a near-zero-gradient weight differently:
+            # compare with a tolerance of a small fraction of lr
+            assert (got_p[n] - ref_p[n]).abs().max() <= 2e-4, (graph, n)
+            assert _cos(got_p[n] - 0, ref_p[n] - 0) > 0.999999, (graph, n)
+
+
 # ----------------------------------------------------------------------------------------------
 # optimal transport (model/ot.py): golden vectors from the unmodified reference + oracle
 # ----------------------------------------------------------------------------------------------
