@@ -225,6 +225,45 @@ embedding_scatter_add_kernel(const bf16* __restrict__ d, const long long* __rest
     }
 }
 
+// Deterministic variant for rows sorted by id: ids_sorted[p] ascending, perm[p] = source row of the
+// p-th sorted entry (stable sort). One warp per RUN of equal ids: it adds the run's rows in sorted order
+// into registers and does one plain read-modify-write of table_grad[id, :] -- no atomics, so identical
+// inputs give bit-identical tables on every rank (data-parallel sparse exchange of the word-embedding
+// gradient, train.py).
+__global__ void __launch_bounds__(256)
+embedding_segment_add_kernel(const bf16* __restrict__ d, const long long* __restrict__ ids_sorted,
+                             const long long* __restrict__ perm, float* __restrict__ table_grad, int n,
+                             int H, long long padding_idx) {
+    pdl_sync();
+    const int lane = threadIdx.x & 31;
+    const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (p >= n) return;
+    const long long id = ids_sorted[p];
+    if (id == padding_idx) return;
+    if (p > 0 && ids_sorted[p - 1] == id) return;  // not the first entry of its run
+    float* dst = table_grad + (size_t)id * H;
+    for (int v = lane; v < (H >> 3); v += 32) {
+        float acc[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+        for (int q = p; q < n && ids_sorted[q] == id; ++q) {
+            uint4 u = *reinterpret_cast<const uint4*>(d + (size_t)perm[q] * H + v * 8);
+            const uint32_t* up = &u.x;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float2 f = unpack_bf16(up[k]);
+                acc[2 * k] += f.x;
+                acc[2 * k + 1] += f.y;
+            }
+        }
+        float4* o = reinterpret_cast<float4*>(dst + v * 8);
+        float4 a = o[0], b = o[1];
+        a.x += acc[0]; a.y += acc[1]; a.z += acc[2]; a.w += acc[3];
+        b.x += acc[4]; b.y += acc[5]; b.z += acc[6]; b.w += acc[7];
+        o[0] = a; o[1] = b;
+    }
+}
+
 // dW[h, c] += sum_r dp[r, h] * pos7[r, c]   (pos_linear weight grad, K = 7). One thread per h.
 __global__ void __launch_bounds__(256)
 pos_linear_wgrad_kernel(const bf16* __restrict__ dp, const float* __restrict__ pos7,
@@ -318,6 +357,19 @@ extern "C" int b200u_embedding_scatter_add(const void* d, const long long* ids, 
     if (n == 0) return B200U_OK;
     launch_k(embedding_scatter_add_kernel, dim3((n + 7) / 8), dim3(256), 0, stream, (const bf16*)d, ids, ids_batch_stride, T, const_id, table_grad, n, H, padding_idx);
     B200U_CHECK_LAUNCH("embedding_scatter_add");
+    return B200U_OK;
+}
+
+extern "C" int b200u_embedding_segment_add(const void* d, const long long* ids_sorted, const long long* perm,
+                                           float* table_grad, int n, int H, long long padding_idx,
+                                           b200u_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    B200U_CHECK_ARG(d && ids_sorted && perm && table_grad, "embedding_segment_add: null pointer");
+    B200U_CHECK_ARG(H % 8 == 0, "embedding_segment_add: H must be a multiple of 8");
+    if (n == 0) return B200U_OK;
+    launch_k(embedding_segment_add_kernel, dim3((n + 7) / 8), dim3(256), 0, stream, (const bf16*)d, ids_sorted,
+             perm, table_grad, n, H, padding_idx);
+    B200U_CHECK_LAUNCH("embedding_segment_add_kernel");
     return B200U_OK;
 }
 

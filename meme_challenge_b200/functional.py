@@ -35,6 +35,7 @@ class Runtime(object):
         self.gemm_impl = gemm_impl
         self.eps = eps
         self.layer_cb = None
+        self.sparse_word_cb = None   # data parallel: takes (d_rows bf16 [n,H], ids [n], padding_idx) instead of the dense scatter
 
     def drop(self, stream_id, p):
         return _lib.dropout_t(self.seed, stream_id, p)
@@ -264,8 +265,14 @@ class TxtEmbedFn(torch.autograd.Function):
                                   grad_buf(emb.LayerNorm.weight), grad_buf(emb.LayerNorm.bias),
                                   drop=ctx.drop, drop_on_input=True)
         pad = emb.word_embeddings.padding_idx
-        ops._call("b200u_embedding_scatter_add", P(dx), P(input_ids), T, T, C.c_longlong(0),
-                  P(grad_buf(emb.word_embeddings.weight)), B * T, H, C.c_longlong(-1 if pad is None else pad))
+        if ctx.rt.sparse_word_cb is not None:
+            # data-parallel last micro-batch: the (at most B*T) touched rows are exchanged between ranks
+            # instead of all-reducing the dense [vocab, H] gradient after the backward pass
+            grad_buf(emb.word_embeddings.weight)
+            ctx.rt.sparse_word_cb(dx, input_ids.reshape(-1), -1 if pad is None else pad)
+        else:
+            ops._call("b200u_embedding_scatter_add", P(dx), P(input_ids), T, T, C.c_longlong(0),
+                      P(grad_buf(emb.word_embeddings.weight)), B * T, H, C.c_longlong(-1 if pad is None else pad))
         ops._call("b200u_embedding_scatter_add", P(dx), P(position_ids), pos_stride, T, C.c_longlong(0),
                   P(grad_buf(emb.position_embeddings.weight)), B * T, H, C.c_longlong(-1))
         tg = grad_buf(emb.token_type_embeddings.weight)

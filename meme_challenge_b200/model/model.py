@@ -256,6 +256,7 @@ class UniterModel(UniterPreTrainedModel):
         rt = F_.Runtime(st, training, seed, self.config.hidden_dropout_prob,
                         self.config.attention_probs_dropout_prob, self.gemm_impl)
         rt.layer_cb = getattr(self, "_layer_grad_ready_cb", None)
+        rt.sparse_word_cb = getattr(self, "_sparse_word_cb", None)
         return rt
 
     # ---------------------------------------------------------------- reference API

@@ -140,6 +140,17 @@ class TrainStep(object):
         self.comm = GradBuckets([(e[0], e[2]) for e in store.entries], store.grad, process_group, self.world)
         self.buckets = self.comm.segments
         self.comm.sync = not overlap_comm
+        # Word-embedding gradient [vocab, H] (20 % of all parameters, produced LAST by every backward, so its
+        # dense all-reduce could not overlap anything): with world_size > 1 the part accumulated by the earlier
+        # micro-batches is all-reduced beside the last backward, and the last micro-batch contributes its
+        # <= B*T touched rows through an all-gather + local scatter-add instead (sparse_word).
+        self.word_slice = None
+        for name, p, off, cnt in store.entries:
+            if name.endswith("embeddings.word_embeddings.weight"):
+                self.word_slice = (off, off + cnt, p)
+        self.sparse_word = True
+        self._word_rows = None
+        self._word_dense = None
         self._graph = None
         self._static = None
         self.um._layer_grad_ready_cb = None
@@ -155,8 +166,9 @@ class TrainStep(object):
         self.comm.reduce_bucket(layer_idx + 1)
 
     # ------------------------------------------------------------------ one micro-batch
-    def _forward_loss(self, batch, last):
-        """Forward + loss of one micro-batch on the current stream. Returns the state `_backward` needs."""
+    def _forward_loss(self, batch, last, first=True):
+        """Forward + loss of one micro-batch on the current stream. Returns the state `_backward` needs.
+        `first`: no earlier micro-batch of this window has accumulated gradients yet."""
         kw = dict(input_ids=batch["input_ids"], position_ids=batch["position_ids"],
                   img_feat=batch["img_feat"], img_pos_feat=batch["img_pos_feat"],
                   attention_mask=batch["attn_mask"], gather_index=batch["gather_index"],
@@ -165,15 +177,26 @@ class TrainStep(object):
         # the layer hooks are registered during the forward (they capture the callback), so it is only
         # set around this call
         self.um._layer_grad_ready_cb = self._on_layer_done if (comm and self.overlap_comm) else None
+        sparse = comm and self.overlap_comm and self.sparse_word and self.word_slice is not None
+        self.um._sparse_word_cb = self._on_word_rows if sparse else None
         try:
             logits = self.model(**kw)
         finally:
             self.um._layer_grad_ready_cb = None
+            self.um._sparse_word_cb = None
         loss, dlogits, probs = F_.bce_with_logits(logits, batch["labels"], self.pos_wt)
-        return logits, dlogits, loss, probs, comm
+        return logits, dlogits, loss, probs, comm, sparse, first
+
+    def _on_word_rows(self, d_rows, ids, pad):
+        self._word_rows = (d_rows, ids.contiguous(), pad)
 
     def _backward(self, state):
-        logits, dlogits, loss, probs, comm = state
+        logits, dlogits, loss, probs, comm, sparse, first = state
+        dist = torch.distributed
+        if sparse and not first:
+            # what the earlier micro-batches left in the word-embedding gradient travels beside this backward
+            lo, hi, _ = self.word_slice
+            self._word_dense = dist.all_reduce(self.store.grad[lo:hi], group=self.pg, async_op=True)
         limit = comm and self.overlap_comm and self.comm_sm_reserve > 0
         if limit:
             sms = C.c_int()
@@ -188,11 +211,40 @@ class TrainStep(object):
             if not self.overlap_comm:
                 for i in range(len(self.buckets) - 1, 0, -1):
                     self._allreduce_bucket(i)
-            self._allreduce_bucket(0)
+            if sparse:
+                self._finish_sparse_word()
+            else:
+                self._allreduce_bucket(0)
         return loss, probs
 
-    def micro_step(self, batch, last):
-        return self._backward(self._forward_loss(batch, last))
+    def _finish_sparse_word(self):
+        """Embedding bucket without the word table (dense, small) + the sparse word-row exchange."""
+        dist = torch.distributed
+        lo, hi, wp = self.word_slice
+        b_lo, b_hi = self.buckets[0]
+        self.comm.reduced.append(0)
+        for a, b in ((b_lo, min(lo, b_hi)), (max(hi, b_lo), b_hi)):
+            if b > a:
+                self.comm.pending.append(dist.all_reduce(self.store.grad[a:b], group=self.pg, async_op=True))
+        rows, ids, pad = self._word_rows
+        self._word_rows = None
+        n, H = rows.shape
+        all_rows = torch.empty(self.world * n, H, device=rows.device, dtype=rows.dtype)
+        all_ids = torch.empty(self.world * n, device=ids.device, dtype=ids.dtype)
+        dist.all_gather_into_tensor(all_rows, rows.contiguous(), group=self.pg)
+        dist.all_gather_into_tensor(all_ids, ids, group=self.pg)
+        if self._word_dense is not None:
+            self._word_dense.wait()       # the scatter below must land on the all-reduced table
+            self._word_dense = None
+        # identical (all_rows, all_ids) on every rank + a deterministic, atomic-free segment add (rows sorted
+        # by id, each run summed in order) => bit-identical word-embedding gradients on all replicas
+        ids_sorted, perm = torch.sort(all_ids, stable=True)
+        tot = self.world * n
+        ops._call("b200u_embedding_segment_add", P(all_rows), P(ids_sorted), P(perm), P(self.store.grad[lo:hi]),
+                  tot, H, C.c_longlong(pad))
+
+    def micro_step(self, batch, last, first=True):
+        return self._backward(self._forward_loss(batch, last, first))
 
     # ------------------------------------------------------------------ optimizer
     def optimizer_step(self):
@@ -225,7 +277,7 @@ class TrainStep(object):
         assert len(batches) == self.accum
         n = len(batches)
         if n == 1 or not self.pipeline:
-            outs = [self.micro_step(b, last=(i == n - 1)) for i, b in enumerate(batches)]
+            outs = [self.micro_step(b, last=(i == n - 1), first=(i == 0)) for i, b in enumerate(batches)]
         else:
             main = torch.cuda.current_stream()
             if self._aux_stream is None:
@@ -238,7 +290,7 @@ class TrainStep(object):
                 if after is not None:
                     s.wait_event(after)
                 with torch.cuda.stream(s):
-                    state[i] = self._forward_loss(batches[i], last=(i == n - 1))
+                    state[i] = self._forward_loss(batches[i], last=(i == n - 1), first=(i == 0))
                     return s.record_event()
 
             def bwd(i, after):

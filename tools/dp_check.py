@@ -1,0 +1,79 @@
+"""torchrun target: data-parallel TrainStep correctness on N GPUs (tiny model, dropout off).
+Checks (1) every rank ends with identical parameters, (2) the sparse word-embedding row exchange gives the
+same parameters as the dense all-reduce path, (3) both equal a single-process run over the union of the
+ranks' micro-batches with gradients averaged the same way (world * accum micro-batches per step)."""
+import os, sys
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+import torch
+import torch.distributed as dist
+from meme_challenge_b200.model.meme_uniter import MemeUniter
+from meme_challenge_b200.model.model import UniterConfig, UniterModel
+from meme_challenge_b200.train import TrainStep
+from oracle import uniter_oracle as O
+from oracle.make_golden import IMG_DIM, TINY
+
+rank, world, lr_ = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(lr_)
+dev = torch.device("cuda", lr_)
+dist.init_process_group("nccl", device_id=dev)
+cfg = dict(TINY); cfg["hidden_dropout_prob"] = 0.0; cfg["attention_probs_dropout_prob"] = 0.0
+
+
+def batch(seed):
+    b = O.synth_batch(4, 12, 10, seed=seed, img_dim=IMG_DIM, vocab=TINY["vocab_size"], min_txt=2, min_bb=2)
+    d = {k: v.to(dev) for k, v in b.items() if torch.is_tensor(v)}
+    d["labels"] = b["labels"].float().to(dev)
+    return d
+
+
+def run(sparse, graph, steps=2):
+    torch.manual_seed(0)
+    m = MemeUniter(UniterModel(UniterConfig.from_dict(cfg), IMG_DIM), cfg["hidden_size"], 1).to(dev).train()
+    ts = TrainStep(m, lr=1e-3, weight_decay=1e-3, gradient_accumulation=2, max_grad_norm=5.0, pos_wt=1.8)
+    ts.sparse_word = sparse
+    if graph:
+        ts.capture([batch(100 + rank * 10), batch(101 + rank * 10)], warmup=0)
+    for s in range(steps):
+        bs = [batch(100 + rank * 10 + 2 * s), batch(101 + rank * 10 + 2 * s)]
+        if graph:
+            ts.load_static(bs); ts.replay()
+        else:
+            ts.step(bs)
+    torch.cuda.synchronize()
+    return torch.cat([p.detach().flatten() for p in m.parameters()])
+
+
+def single(steps=2):
+    """one process, the union of all ranks' micro-batches: grads summed, / (accum * world), clip, Adam"""
+    torch.manual_seed(0)
+    m = MemeUniter(UniterModel(UniterConfig.from_dict(cfg), IMG_DIM), cfg["hidden_size"], 1).to(dev).train()
+    ts = TrainStep(m, lr=1e-3, weight_decay=1e-3, gradient_accumulation=2 * world, max_grad_norm=5.0, pos_wt=1.8,
+                   process_group=None)
+    ts.world = 1
+    for s in range(steps):
+        bs = []
+        for r in range(world):
+            bs += [batch(100 + r * 10 + 2 * s), batch(101 + r * 10 + 2 * s)]
+        ts.pipeline = False
+        ts.step(bs)
+    torch.cuda.synchronize()
+    return torch.cat([p.detach().flatten() for p in m.parameters()])
+
+
+ok = True
+ref = single() if rank == 0 else None
+for sparse in (False, True):
+    for graph in (False, True):
+        p = run(sparse, graph)
+        gathered = [torch.empty_like(p) for _ in range(world)]
+        dist.all_gather(gathered, p)
+        same = all(torch.equal(gathered[0], g) for g in gathered)
+        if rank == 0:
+            err = (p - ref).abs().max().item()
+            print("sparse=%d graph=%d ranks_identical=%s max|p - single_process|=%.3e" % (sparse, graph, same, err), flush=True)
+            ok = ok and same and err < 2e-4
+dist.barrier()
+if rank == 0:
+    print("DP CHECK", "PASS" if ok else "FAIL", flush=True)
+torch.cuda.synchronize()
+os._exit(0 if ok else 1)
