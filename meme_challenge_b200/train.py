@@ -141,9 +141,10 @@ class TrainStep(object):
         self.buckets = self.comm.segments
         self.comm.sync = not overlap_comm
         # Word-embedding gradient [vocab, H] (20 % of all parameters, produced LAST by every backward, so its
-        # dense all-reduce could not overlap anything): with world_size > 1 the part accumulated by the earlier
-        # micro-batches is all-reduced beside the last backward, and the last micro-batch contributes its
-        # <= B*T touched rows through an all-gather + local scatter-add instead (sparse_word).
+        # dense all-reduce could not overlap anything, and row-sparse: <= B*T rows per micro-batch): with
+        # world_size > 1 the micro-batches hand their touched rows over instead of scattering them, and after
+        # the last backward the rows of the whole window are all-gathered and applied by every rank with a
+        # deterministic segment add (sparse_word). No dense all-reduce of the table at all.
         self.word_slice = None
         for name, p, off, cnt in store.entries:
             if name.endswith("embeddings.word_embeddings.weight"):
@@ -177,7 +178,11 @@ class TrainStep(object):
         # the layer hooks are registered during the forward (they capture the callback), so it is only
         # set around this call
         self.um._layer_grad_ready_cb = self._on_layer_done if (comm and self.overlap_comm) else None
-        sparse = comm and self.overlap_comm and self.sparse_word and self.word_slice is not None
+        # data parallel: EVERY micro-batch of the window hands its touched word-embedding rows over instead of
+        # scattering them into the dense table; they are exchanged together after the last backward
+        sparse = (self.world > 1 and self.overlap_comm and self.sparse_word and self.word_slice is not None)
+        if sparse and first:
+            self._word_rows = []
         self.um._sparse_word_cb = self._on_word_rows if sparse else None
         try:
             logits = self.model(**kw)
@@ -188,15 +193,11 @@ class TrainStep(object):
         return logits, dlogits, loss, probs, comm, sparse, first
 
     def _on_word_rows(self, d_rows, ids, pad):
-        self._word_rows = (d_rows, ids.contiguous(), pad)
+        self._word_rows.append((d_rows, ids.contiguous(), pad))
 
     def _backward(self, state):
         logits, dlogits, loss, probs, comm, sparse, first = state
         dist = torch.distributed
-        if sparse and not first:
-            # what the earlier micro-batches left in the word-embedding gradient travels beside this backward
-            lo, hi, _ = self.word_slice
-            self._word_dense = dist.all_reduce(self.store.grad[lo:hi], group=self.pg, async_op=True)
         limit = comm and self.overlap_comm and self.comm_sm_reserve > 0
         if limit:
             sms = C.c_int()
@@ -215,6 +216,7 @@ class TrainStep(object):
                 self._finish_sparse_word()
             else:
                 self._allreduce_bucket(0)
+
         return loss, probs
 
     def _finish_sparse_word(self):
@@ -226,16 +228,19 @@ class TrainStep(object):
         for a, b in ((b_lo, min(lo, b_hi)), (max(hi, b_lo), b_hi)):
             if b > a:
                 self.comm.pending.append(dist.all_reduce(self.store.grad[a:b], group=self.pg, async_op=True))
-        rows, ids, pad = self._word_rows
+        pad = self._word_rows[0][2]
+        cur = torch.cuda.current_stream()
+        for r, i, _ in self._word_rows:      # earlier micro-batches produced their rows on the other stream
+            r.record_stream(cur)
+            i.record_stream(cur)
+        rows = torch.cat([r for r, _, _ in self._word_rows], 0)
+        ids = torch.cat([i for _, i, _ in self._word_rows], 0)
         self._word_rows = None
         n, H = rows.shape
         all_rows = torch.empty(self.world * n, H, device=rows.device, dtype=rows.dtype)
         all_ids = torch.empty(self.world * n, device=ids.device, dtype=ids.dtype)
         dist.all_gather_into_tensor(all_rows, rows.contiguous(), group=self.pg)
         dist.all_gather_into_tensor(all_ids, ids, group=self.pg)
-        if self._word_dense is not None:
-            self._word_dense.wait()       # the scatter below must land on the all-reduced table
-            self._word_dense = None
         # identical (all_rows, all_ids) on every rank + a deterministic, atomic-free segment add (rows sorted
         # by id, each run summed in order) => bit-identical word-embedding gradients on all replicas
         ids_sorted, perm = torch.sort(all_ids, stable=True)
