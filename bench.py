@@ -7,10 +7,16 @@ on BASELINE config 2: gradient_accumulation = 2 micro-batches of 16 memes (100 r
 + 7-d boxes, 64 tokens, joint length 164), each forward + backward with dropout 0.1 and the
 pos_wt 1.8 BCE loss, then grad averaging, clip_grad_norm_(5), Adam(L2 1e-3) and zero_grad.
 Synthetic data, random-init weights. `value` times K steps with the inputs already
-resident in HBM (CUDA-graph replay); `e2e` times the same steps through the public TrainStep API
-fed from pinned HOST buffers, including the H2D copies and a D2H read of the loss every step.
+resident in HBM (CUDA-graph replay of the whole step); `e2e` times the same steps through the public
+TrainStep API fed from pinned HOST buffers: the H2D copy of step i+1 overlaps step i on a copy stream,
+every step refreshes the graph's inputs and reads its loss back (D2H). `roofline` times every GEMM
+shape of the step live (CUDA events around captured back-to-back launches) against the measured
+sustained bf16 peak; `cpu_baseline` times the oracle port of the reference's CPU path on the host cores.
 For N > 1 run under torchrun (one rank per GPU, NCCL): each rank processes its own 16-meme
-micro-batches (weak scaling) and gradient buckets are all-reduced overlapped with backward.
+micro-batches (weak scaling); the per-layer gradient all-reduces and the sparse word-embedding row
+exchange are captured in the same CUDA graph and overlap the last backward pass.
+`--impl reference` times the reference's CPU implementation (oracle port) on the host cores.
+Only the result line is written to stdout.
 """
 import argparse
 import json
