@@ -55,32 +55,6 @@ int gemm(int M, int N, int K, const void* A, int lda, int a_mn, const void* B, i
 
 }  // namespace
 
-extern "C" int b200u_bert_layer_fwd(const b200u_layer_params_t* p, const void* x0,
-                                    const b200u_layer_saved_t* s, void* x2, b200u_stream_t stream_) {
-    cudaStream_t st = (cudaStream_t)stream_;
-    B200U_CHECK_ARG(p && x0 && s && x2, "bert_layer_fwd: null pointer");
-    const int M = p->B * p->L, H = p->H, I = p->I;
-    if (M == 0) return B200U_OK;
-    const b200u_dropout_t d_attn = site(p, SITE_ATTN, p->p_attn);
-    const b200u_dropout_t d_h1 = site(p, SITE_HID1, p->p_hidden);
-    const b200u_dropout_t d_h2 = site(p, SITE_HID2, p->p_hidden);
-
-    TRY(gemm(M, 3 * H, H, x0, H, 0, p->Wqkv, H, 0, B200U_EPI_STORE, s->qkv, 3 * H, nullptr, 0, p->bqkv,
-             nullptr, 0, nullptr, p->gemm_impl, st));
-    TRY(b200u_attention_fwd(s->qkv, p->mask, s->ctx, s->lse, p->B, p->L, p->heads, H, &d_attn, st));
-    TRY(gemm(M, H, H, s->ctx, H, 0, p->Wo, H, 0, B200U_EPI_BIAS_DROP_RES, s->y1, H, nullptr, 0, p->bo, x0,
-             H, &d_h1, p->gemm_impl, st));
-    TRY(b200u_layernorm_fwd(s->y1, B200U_BF16, p->ln1_g, p->ln1_b, s->x1, B200U_BF16, s->mean1, s->rstd1,
-                            M, H, p->eps, nullptr, st));
-    TRY(gemm(M, I, H, s->x1, H, 0, p->W1, H, 0, B200U_EPI_BIAS_GELU, s->u, I, s->g, I, p->b1, nullptr, 0,
-             nullptr, p->gemm_impl, st));
-    TRY(gemm(M, H, I, s->g, I, 0, p->W2, I, 0, B200U_EPI_BIAS_DROP_RES, s->y2, H, nullptr, 0, p->b2, s->x1,
-             H, &d_h2, p->gemm_impl, st));
-    TRY(b200u_layernorm_fwd(s->y2, B200U_BF16, p->ln2_g, p->ln2_b, x2, B200U_BF16, s->mean2, s->rstd2, M,
-                            H, p->eps, nullptr, st));
-    return B200U_OK;
-}
-
 // ---- side stream for the weight-gradient GEMMs of the backward pass -------------------------------
 // dW GEMMs (and the b1 bias-gradient column sum) are off the critical path: nothing in the layer's
 // backward chain consumes them. They run on a library-owned side stream, forked from / joined to the
@@ -127,6 +101,33 @@ SideCtx* side_ctx() {
 
 extern "C" int b200u_set_bwd_streams(int two_streams) {
     g_side_mode = two_streams ? 1 : 0;
+    return B200U_OK;
+}
+
+extern "C" int b200u_bert_layer_fwd(const b200u_layer_params_t* p, const void* x0,
+                                    const b200u_layer_saved_t* s, void* x2, b200u_stream_t stream_) {
+    cudaStream_t st = (cudaStream_t)stream_;
+    B200U_CHECK_ARG(p && x0 && s && x2, "bert_layer_fwd: null pointer");
+    const int M = p->B * p->L, H = p->H, I = p->I;
+    if (M == 0) return B200U_OK;
+    const b200u_dropout_t d_attn = site(p, SITE_ATTN, p->p_attn);
+    const b200u_dropout_t d_h1 = site(p, SITE_HID1, p->p_hidden);
+    const b200u_dropout_t d_h2 = site(p, SITE_HID2, p->p_hidden);
+    if (g_side_mode) side_ctx();  // create the backward's side stream / events outside any later capture
+
+    TRY(gemm(M, 3 * H, H, x0, H, 0, p->Wqkv, H, 0, B200U_EPI_STORE, s->qkv, 3 * H, nullptr, 0, p->bqkv,
+             nullptr, 0, nullptr, p->gemm_impl, st));
+    TRY(b200u_attention_fwd(s->qkv, p->mask, s->ctx, s->lse, p->B, p->L, p->heads, H, &d_attn, st));
+    TRY(gemm(M, H, H, s->ctx, H, 0, p->Wo, H, 0, B200U_EPI_BIAS_DROP_RES, s->y1, H, nullptr, 0, p->bo, x0,
+             H, &d_h1, p->gemm_impl, st));
+    TRY(b200u_layernorm_fwd(s->y1, B200U_BF16, p->ln1_g, p->ln1_b, s->x1, B200U_BF16, s->mean1, s->rstd1,
+                            M, H, p->eps, nullptr, st));
+    TRY(gemm(M, I, H, s->x1, H, 0, p->W1, H, 0, B200U_EPI_BIAS_GELU, s->u, I, s->g, I, p->b1, nullptr, 0,
+             nullptr, p->gemm_impl, st));
+    TRY(gemm(M, H, I, s->g, I, 0, p->W2, I, 0, B200U_EPI_BIAS_DROP_RES, s->y2, H, nullptr, 0, p->b2, s->x1,
+             H, &d_h2, p->gemm_impl, st));
+    TRY(b200u_layernorm_fwd(s->y2, B200U_BF16, p->ln2_g, p->ln2_b, x2, B200U_BF16, s->mean2, s->rstd2, M,
+                            H, p->eps, nullptr, st));
     return B200U_OK;
 }
 
