@@ -94,3 +94,24 @@ def test_no_cpu_fallback(built_lib):
         m(input_ids=b["input_ids"], position_ids=b["position_ids"], img_feat=b["img_feat"],
           img_pos_feat=b["img_pos_feat"], attention_mask=b["attn_mask"], gather_index=b["gather_index"],
           output_all_encoded_layers=False)
+
+
+def test_bench_reference_arm_emits_one_contract_line():
+    """`bench.py --impl reference` (the reference's CPU path = the oracle port, no GPU needed) prints exactly
+    ONE JSON line on stdout carrying the contract keys; everything else goes to stderr."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
+                        "--warmup", "1"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "memes/s" and d["higher_is_better"] is True
+    assert d["metric"] == "UNITER-base fwd+bwd memes/s" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": "memes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"] and "model" not in d["config"]
