@@ -47,6 +47,9 @@ int b200u_set_sm_limit(int n);
  * side stream forked from / joined to the caller's stream with events (capturable), so they fill the
  * SMs the critical-path kernels leave idle; 0 = everything on the caller's stream. */
 int b200u_set_bwd_streams(int two_streams);
+/* b200u_bert_layer_fwd: 1 (default) = residual + LayerNorm inside the attn-out / FFN2 GEMM epilogues
+ * (EPI_BIAS_DROP_RES_LN, 5 launches per layer); 0 = LayerNorm as its own launch (7 launches). */
+int b200u_set_fused_layernorm(int on);
 /* Event-time every tcgen05 GEMM launch (bench.py roofline leg). enable(n) arms up to n records,
  * collect() synchronises and returns summed duration / algorithmic FLOPs (2MNK) / record count.
  * Must not be armed during CUDA-graph capture. */
@@ -80,7 +83,17 @@ enum {
     B200U_EPI_DGELU = 4,         /* C(bf16) = acc * gelu_erf'(R)                              */
     B200U_EPI_ATOMIC_F32 = 5,    /* C(f32) += acc   (split-K safe; wgrad into .grad buffers)  */
     B200U_EPI_STORE_F32 = 6,     /* C(f32) = acc (+ bias)                                     */
-    B200U_EPI_COUNT = 7
+    B200U_EPI_BIAS_GELU_DG = 7,  /* u = acc + bias ; C(bf16) = gelu_erf'(u) ; C2(bf16) = gelu_erf(u):
+                                    the FFN1 forward saves the DERIVATIVE instead of the pre-activation,
+                                    so the backward epilogue is a plain multiply (EPI_MUL)           */
+    B200U_EPI_MUL = 8,           /* C(bf16) = acc * R ; optional colsum[n] += sum_m C(m,n) (bias grad) */
+    B200U_EPI_BIAS_DROP_RES_LN = 9, /* y = dropout(acc + bias) + R -> C(bf16) ; C2(bf16) = LayerNorm(y)
+                                    over the full row (N = 128 * cluster size <= 1024): the CTAs that own
+                                    the N/128 column tiles of one row block form a thread-block cluster and
+                                    exchange row statistics through distributed shared memory;
+                                    ln_mean / ln_rstd (f32 [M]) are saved for the backward
+                                    (model/layer.py:111-115,152-156)                                  */
+    B200U_EPI_COUNT = 10
 };
 
 typedef struct {
@@ -97,6 +110,12 @@ typedef struct {
     int block_n;            /* 0 = auto, else 128 or 256 */
     int impl;               /* 0 = tcgen05 (product path), 1 = SIMT debug kernel */
     int cluster;            /* 0 = auto, 1 = no cluster, 2 = CTA pairs with TMA-multicast B tiles */
+    float* colsum;          /* EPI_MUL: f32 [N] or NULL, += column sums of the bf16 output */
+    const float* ln_gamma;  /* EPI_BIAS_DROP_RES_LN: f32 [N] LayerNorm weight / bias, eps, saved statistics */
+    const float* ln_beta;
+    float* ln_mean;         /* f32 [M] or NULL */
+    float* ln_rstd;         /* f32 [M] or NULL */
+    float ln_eps;
 } b200u_gemm_t;
 
 int b200u_gemm(const b200u_gemm_t* g, b200u_stream_t stream);
@@ -215,7 +234,7 @@ typedef struct {
     void* y1;   /* bf16 [M,H] pre-LN1 */
     float* mean1; float* rstd1;
     void* x1;   /* bf16 [M,H] LN1 out */
-    void* u;    /* bf16 [M,I] pre-GELU */
+    void* u;    /* bf16 [M,I] gelu'(pre-activation): the derivative, not the pre-activation, is saved */
     void* g;    /* bf16 [M,I] post-GELU */
     void* y2;   /* bf16 [M,H] pre-LN2 */
     float* mean2; float* rstd2;

@@ -35,10 +35,18 @@ class GemmT(C.Structure):
         ("R", C.c_void_p), ("ldr", C.c_int),
         ("drop", DropoutT),
         ("splits", C.c_int), ("block_n", C.c_int), ("impl", C.c_int), ("cluster", C.c_int),
+        ("colsum", C.c_void_p),
+        ("ln_gamma", C.c_void_p), ("ln_beta", C.c_void_p), ("ln_mean", C.c_void_p), ("ln_rstd", C.c_void_p),
+        ("ln_eps", C.c_float),
     ]
 
 
-EPI_STORE, EPI_BIAS_GELU, EPI_BIAS_DROP_RES, EPI_ADD, EPI_DGELU, EPI_ATOMIC_F32, EPI_STORE_F32 = range(7)
+(EPI_STORE, EPI_BIAS_GELU, EPI_BIAS_DROP_RES, EPI_ADD, EPI_DGELU, EPI_ATOMIC_F32, EPI_STORE_F32,
+ EPI_BIAS_GELU_DG, EPI_MUL, EPI_BIAS_DROP_RES_LN) = range(10)
+EPI_COUNT = 10
+EPI_HAS_BIAS = (EPI_STORE, EPI_BIAS_GELU, EPI_BIAS_DROP_RES, EPI_STORE_F32, EPI_BIAS_GELU_DG, EPI_BIAS_DROP_RES_LN)
+EPI_HAS_RES = (EPI_BIAS_DROP_RES, EPI_ADD, EPI_DGELU, EPI_MUL, EPI_BIAS_DROP_RES_LN)
+EPI_DUAL = (EPI_BIAS_GELU, EPI_BIAS_GELU_DG, EPI_BIAS_DROP_RES_LN)
 
 
 def lib():

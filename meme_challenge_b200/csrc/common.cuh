@@ -218,6 +218,24 @@ __device__ __forceinline__ f32x2 gelu_grad_pair(f32x2 x) {
     const f32x2 cdf = f2_add(sg, f2s(0.5f));
     return f2_fma(f2_mul(x, e), f2s(0.39894228040143267794f), cdf);
 }
+// gelu'(x) (returned) and gelu(x) (val) from one erfc / exp evaluation: the FFN1 forward epilogue saves
+// the derivative so the backward epilogue is a plain multiply.
+__device__ __forceinline__ f32x2 gelu_both_pair(f32x2 x, f32x2& val) {
+    float x0, x1;
+    f2_get(x, x0, x1);
+    const f32x2 ax = f2(fabsf(x0), fabsf(x1));
+    f32x2 e;
+    const f32x2 q = erfc_pair<1>(ax, e);                 // erfc(|x| / sqrt 2), e = exp(-x^2 / 2)
+    const f32x2 hq = f2_fma(q, f2s(-0.5f), f2s(0.5f));   // 1/2 - q/2 in [0, 1/2]
+    float q0, q1;
+    f2_get(hq, q0, q1);
+    const f32x2 sg = f2(__uint_as_float(__float_as_uint(q0) | (__float_as_uint(x0) & 0x80000000u)),
+                        __uint_as_float(__float_as_uint(q1) | (__float_as_uint(x1) & 0x80000000u)));
+    const f32x2 cdf = f2_add(sg, f2s(0.5f));             // Phi(x)
+    // gelu(x) = relu(x) - |x|/2 * erfc(|x| / sqrt 2): no cancellation for negative x
+    val = f2_fma(f2_mul(ax, q), f2s(-0.5f), f2_mul(f2_add(x, ax), f2s(0.5f)));
+    return f2_fma(f2_mul(x, e), f2s(0.39894228040143267794f), cdf);
+}
 __device__ __forceinline__ float gelu_erf(float x) {
     float lo, hi;
     f2_get(gelu_pair(f2(x, x)), lo, hi);
@@ -371,6 +389,46 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+    return r;
+}
+// ---- distributed shared memory: address of the same smem location in CTA `rank` of the cluster, remote
+// stores, remote mbarrier arrival (release at cluster scope) and the matching acquire-wait
+__device__ __forceinline__ uint32_t dsmem_addr(uint32_t local_saddr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_saddr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void dsmem_st_f32x2(uint32_t raddr, float a, float b) {
+    asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(raddr), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ void dsmem_mbar_arrive(uint32_t rbar) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(rbar) : "memory");
+}
+// remote 8-byte store that completes 8 transaction bytes on the (remote) mbarrier `rbar` when it lands:
+// the data and its arrival signal travel together, no fence / separate arrive needed
+__device__ __forceinline__ void dsmem_st_async_f32x2(uint32_t raddr, float a, float b, uint32_t rbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];"
+                 ::"r"(raddr), "f"(a), "f"(b), "r"(rbar) : "memory");
+}
+__device__ __forceinline__ void fence_acq_rel_cluster() { asm volatile("fence.acq_rel.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
 }
 
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tmap) {

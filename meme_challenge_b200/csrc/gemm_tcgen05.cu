@@ -17,6 +17,8 @@
 
 #include <cudaTypedefs.h>
 
+#include <mutex>
+
 namespace b200u {
 
 struct GemmArgs {
@@ -28,6 +30,10 @@ struct GemmArgs {
     const float* bias;
     const bf16* R; int ldr;
     DropoutCfg drop;
+    float* colsum;                       // EPI_MUL: += column sums of the bf16 output (bias gradient), may be null
+    const float* ln_gamma; const float* ln_beta;  // EPI_BIAS_DROP_RES_LN
+    float* ln_mean; float* ln_rstd; float ln_eps;
+    int ln_cl;                           // EPI_BIAS_DROP_RES_LN: CTAs per cluster = N / 128 column tiles of one row block
     long long* dbg;  // optional per-CTA phase timestamps (8 x int64 per CTA), bring-up only
     int dbg_mode;    // bring-up: 1 = skip the MMAs (TMA-only), 2 = skip the TMA loads (MMA-only)
 };
@@ -57,7 +63,7 @@ __device__ __forceinline__ void epilogue_row32(const float (&acc)[32], int row, 
         for (int i = 0; i < 8; ++i) v[i] = acc[c + i];
 
         if (EPI == B200U_EPI_STORE || EPI == B200U_EPI_BIAS_GELU || EPI == B200U_EPI_BIAS_DROP_RES ||
-            EPI == B200U_EPI_STORE_F32) {
+            EPI == B200U_EPI_STORE_F32 || EPI == B200U_EPI_BIAS_GELU_DG) {
             if (g.bias) {
                 if (full) {
                     float4 b0 = *reinterpret_cast<const float4*>(g.bias + col0 + c);
@@ -70,7 +76,7 @@ __device__ __forceinline__ void epilogue_row32(const float (&acc)[32], int row, 
             }
         }
         float r[8];
-        if (EPI == B200U_EPI_BIAS_DROP_RES || EPI == B200U_EPI_ADD || EPI == B200U_EPI_DGELU) {
+        if (EPI == B200U_EPI_BIAS_DROP_RES || EPI == B200U_EPI_ADD || EPI == B200U_EPI_DGELU || EPI == B200U_EPI_MUL) {
             const bf16* rp = g.R + (size_t)row * g.ldr + col0 + c;
             if (full) {
                 uint4 u = *reinterpret_cast<const uint4*>(rp);
@@ -102,6 +108,12 @@ __device__ __forceinline__ void epilogue_row32(const float (&acc)[32], int row, 
         } else if (EPI == B200U_EPI_DGELU) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] *= gelu_erf_grad(r[i]);
+        } else if (EPI == B200U_EPI_MUL) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                v[i] *= r[i];
+                if (g.colsum && c + i < ncols) atomicAdd(g.colsum + col0 + c + i, __bfloat162float(__float2bfloat16(v[i])));
+            }
         }
 
         if (EPI == B200U_EPI_ATOMIC_F32) {
@@ -129,6 +141,15 @@ __device__ __forceinline__ void epilogue_row32(const float (&acc)[32], int row, 
                 *reinterpret_cast<uint4*>(cp) = o;
             } else {
                 for (int i = 0; i < 8 && c + i < ncols; ++i) cp[i] = __float2bfloat16(v[i]);
+            }
+            if (EPI == B200U_EPI_BIAS_GELU_DG) {
+                // C = gelu'(u) and C2 = gelu(u), both of the bf16-rounded pre-activation u
+                bf16* gp = reinterpret_cast<bf16*>(g.C2) + (size_t)row * g.ldc2 + col0 + c;
+                for (int i = 0; i < 8 && c + i < ncols; ++i) {
+                    const float u = __bfloat162float(__float2bfloat16(v[i]));
+                    cp[i] = __float2bfloat16(gelu_erf_grad(u));
+                    gp[i] = __float2bfloat16(gelu_erf(u));
+                }
             }
             if (EPI == B200U_EPI_BIAS_GELU) {
                 bf16* gp = reinterpret_cast<bf16*>(g.C2) + (size_t)row * g.ldc2 + col0 + c;
@@ -192,11 +213,14 @@ constexpr int GEMM_THREADS = (4 + EPI_WARPS) * 32;  // 384
 
 template <int BLOCK_N, int EPI>
 struct GemmCfg {
-    static constexpr bool HAS_R = EPI == B200U_EPI_BIAS_DROP_RES || EPI == B200U_EPI_ADD || EPI == B200U_EPI_DGELU;
-    static constexpr bool DUAL = EPI == B200U_EPI_BIAS_GELU;
+    static constexpr bool LN = EPI == B200U_EPI_BIAS_DROP_RES_LN;
+    static constexpr bool HAS_R = EPI == B200U_EPI_BIAS_DROP_RES || EPI == B200U_EPI_ADD || EPI == B200U_EPI_DGELU ||
+                                  EPI == B200U_EPI_MUL || LN;
+    static constexpr bool DUAL = EPI == B200U_EPI_BIAS_GELU || EPI == B200U_EPI_BIAS_GELU_DG;
     static constexpr bool F32_OUT = EPI == B200U_EPI_ATOMIC_F32 || EPI == B200U_EPI_STORE_F32;
     static constexpr bool HAS_BIAS = EPI == B200U_EPI_STORE || EPI == B200U_EPI_BIAS_GELU ||
-                                     EPI == B200U_EPI_BIAS_DROP_RES || EPI == B200U_EPI_STORE_F32;
+                                     EPI == B200U_EPI_BIAS_DROP_RES || EPI == B200U_EPI_STORE_F32 ||
+                                     EPI == B200U_EPI_BIAS_GELU_DG || LN;
     static constexpr int GROUP_COLS = F32_OUT ? 32 : 64;  // one 128-byte swizzled row per output group
     static constexpr int NUM_GROUPS = BLOCK_N / GROUP_COLS;
     static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
@@ -209,7 +233,12 @@ struct GemmCfg {
     static constexpr int R_GROUP_BYTES = BLOCK_M * 128;  // side input: one [128 x 64] bf16 box per group
     static constexpr int R_BYTES = HAS_R ? NUM_GROUPS * R_GROUP_BYTES : 0;
     static constexpr int BIAS_BYTES = 2 * BLOCK_N * 4;  // one slot per accumulator stage
-    static constexpr int FIXED = STG_BYTES + R_BYTES + BIAS_BYTES + 256 /*barriers*/;
+    // LayerNorm epilogue: gamma / beta slices of this CTA's columns + the row-statistics mailboxes the
+    // cluster's CTAs push into: [2 buffers][8 source CTAs][2 column groups][128 rows] x (sum, M2)
+    static constexpr int LN_MAX_CL = 8;
+    static constexpr int LN_PART_BYTES = LN ? 2 * LN_MAX_CL * 2 * BLOCK_M * 8 : 0;
+    static constexpr int LN_BYTES = LN ? LN_PART_BYTES + 2 * BLOCK_N * 4 : 0;
+    static constexpr int FIXED = STG_BYTES + R_BYTES + BIAS_BYTES + LN_BYTES + 256 /*barriers*/;
     static constexpr int STAGES_RAW = (232448 - FIXED) / STAGE_BYTES;
     static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
     static_assert(STAGES >= 2, "not enough shared memory for a pipelined main loop");
@@ -227,7 +256,8 @@ __device__ __forceinline__ void epi_math8(const uint32_t* acc, const float* bias
     f32x2 v[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) v[i] = f2(__uint_as_float(acc[2 * i]), __uint_as_float(acc[2 * i + 1]));
-    if (EPI == B200U_EPI_STORE || EPI == B200U_EPI_BIAS_GELU || EPI == B200U_EPI_BIAS_DROP_RES) {
+    if (EPI == B200U_EPI_STORE || EPI == B200U_EPI_BIAS_GELU || EPI == B200U_EPI_BIAS_DROP_RES ||
+        EPI == B200U_EPI_BIAS_GELU_DG || EPI == B200U_EPI_BIAS_DROP_RES_LN) {
         const float4 b0 = *reinterpret_cast<const float4*>(bias8);
         const float4 b1 = *reinterpret_cast<const float4*>(bias8 + 4);
         v[0] = f2_add(v[0], f2(b0.x, b0.y));
@@ -244,14 +274,26 @@ __device__ __forceinline__ void epi_math8(const uint32_t* acc, const float* bias
             out[i] = f2_to_bf16x2(v[i]);
             out2[i] = f2_to_bf16x2(gelu_pair(f2_from_bf16x2(out[i])));
         }
+    } else if (EPI == B200U_EPI_BIAS_GELU_DG) {
+        // derivative AND value of GELU at the bf16-rounded pre-activation (they share erfc / exp)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            f32x2 gval;
+            const f32x2 gder = gelu_both_pair(f2_from_bf16x2(f2_to_bf16x2(v[i])), gval);
+            out[i] = f2_to_bf16x2(gder);
+            out2[i] = f2_to_bf16x2(gval);
+        }
     } else if (EPI == B200U_EPI_DGELU) {
 #pragma unroll
         for (int i = 0; i < 4; ++i)
             out[i] = f2_to_bf16x2(f2_mul(v[i], gelu_grad_pair(f2_from_bf16x2(rr[i]))));
+    } else if (EPI == B200U_EPI_MUL) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) out[i] = f2_to_bf16x2(f2_mul(v[i], f2_from_bf16x2(rr[i])));
     } else if (EPI == B200U_EPI_ADD) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) out[i] = f2_to_bf16x2(f2_add(v[i], f2_from_bf16x2(rr[i])));
-    } else if (EPI == B200U_EPI_BIAS_DROP_RES) {
+    } else if (EPI == B200U_EPI_BIAS_DROP_RES || EPI == B200U_EPI_BIAS_DROP_RES_LN) {
         if (g.drop.thresh16) {
             const uint32_t pbase = (uint32_t)(((size_t)row * g.N + col) >> 1);
 #pragma unroll
@@ -291,13 +333,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint8_t* sR = sB + STAGES * Cfg::B_BYTES;
     uint8_t* sStg = sR + Cfg::R_BYTES;
     float* sBias = reinterpret_cast<float*>(sStg + Cfg::STG_BYTES);
-    uint64_t* full = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sBias) + Cfg::BIAS_BYTES);
+    float* sGam = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(sBias) + Cfg::BIAS_BYTES);  // LN: gamma | beta slices
+    float2* sPart = reinterpret_cast<float2*>(sGam + (Cfg::LN ? 2 * BLOCK_N : 0));                // LN: statistics mailboxes
+    uint64_t* full = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sBias) + Cfg::BIAS_BYTES + Cfg::LN_BYTES);
     uint64_t* empty = full + STAGES;
     uint64_t* tfull = empty + STAGES;
     uint64_t* tempty = tfull + 2;
     uint64_t* rfull = tempty + 2;   // [4] one per side-input group
     uint64_t* rempty = rfull + 4;   // [4]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rempty + 4);
+    uint64_t* lnbar = rempty + 4;   // [2] LN: all CTAs of the cluster have pushed their statistics (per mailbox buffer)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(lnbar + 2);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -308,7 +353,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
         tma_prefetch_desc(&tmC);
-        if (Cfg::DUAL) tma_prefetch_desc(&tmC2);
+        if (Cfg::DUAL || Cfg::LN) tma_prefetch_desc(&tmC2);
         if (Cfg::HAS_R) tma_prefetch_desc(&tmR);
     }
     if (warp == 1 && lane == 0) {
@@ -324,11 +369,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_init(&rfull[a], 1);
             mbar_init(&rempty[a], 4);  // the four quadrant warps that own this group
         }
+        if (Cfg::LN) {
+            mbar_init(&lnbar[0], 1);  // armed per tile with the byte count of the cluster's statistics exchange
+            mbar_init(&lnbar[1], 1);
+        }
         fence_mbar_init();
     }
     if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
     tc_fence_before();
-    if (CLUSTER > 1) cluster_sync_all(); else __syncthreads();
+    // (clusters: no CTA may multicast into / arrive on a peer's barriers before the peer initialised them)
+    if (CLUSTER > 1 || Cfg::LN) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     // everything above (barrier init, TMEM allocation, descriptor prefetch) overlaps the tail of
@@ -336,14 +386,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     pdl_sync();
     if (threadIdx.x == 0) DBG_STAMP(1);
 
-    // work units: (m-tile group of CLUSTER tiles, n-tile, k-split); a cluster walks units together
+    // work units: (m-tile group of CLUSTER tiles, n-tile, k-split); a cluster walks units together.
+    // LayerNorm epilogue: a unit is one 128-row block, the cluster's CTA r owns its column tile r.
     const int cta_rank = CLUSTER > 1 ? (int)cluster_ctarank() : 0;
+    const int ln_rank = Cfg::LN ? (int)cluster_ctarank() : 0;
+    const int ucl = Cfg::LN ? g.ln_cl : CLUSTER;  // CTAs that walk the unit list together
     const int m_groups = (g.m_tiles + CLUSTER - 1) / CLUSTER;
-    const int tiles_mn = m_groups * g.n_tiles;
+    const int tiles_mn = Cfg::LN ? g.m_tiles : m_groups * g.n_tiles;
     const int total_tiles = tiles_mn * g.splits;
-    const int unit0 = blockIdx.x / CLUSTER;
-    const int unit_stride = gridDim.x / CLUSTER;
+    const int unit0 = blockIdx.x / ucl;
+    const int unit_stride = gridDim.x / ucl;
     constexpr uint16_t MC_MASK = (uint16_t)((1u << CLUSTER) - 1);
+    // origin of the output tile of unit `rem` (index inside one k-split)
+    auto tile_origin = [&](int rem, int& m0, int& n0) {
+        if (Cfg::LN) {
+            m0 = rem * BLOCK_M;
+            n0 = ln_rank * BLOCK_N;
+        } else {
+            m0 = ((rem % m_groups) * CLUSTER + cta_rank) * BLOCK_M;
+            n0 = (rem / m_groups) * BLOCK_N;
+        }
+    };
 
     if (warp == 0) {
         // ================= TMA producer =================
@@ -367,11 +430,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         uint32_t rpar = 0;  // bit g: parity of the next use of group g's barriers
         int t_cur = unit0;
         int rm0 = 0, rn0 = 0;  // tile origin of the cursor (divisions only when the cursor moves)
-        auto r_origin = [&]() {
-            const int rrem = rt % tiles_mn;
-            rm0 = ((rrem % m_groups) * CLUSTER + cta_rank) * BLOCK_M;
-            rn0 = (rrem / m_groups) * BLOCK_N;
-        };
+        auto r_origin = [&]() { tile_origin(rt % tiles_mn, rm0, rn0); };
         if (Cfg::HAS_R) r_origin();
         auto r_pump = [&](bool block) {
             if (!Cfg::HAS_R) return;
@@ -402,8 +461,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             t_cur = t;
             const int split = t / tiles_mn;
             const int rem = t - split * tiles_mn;
-            const int m0 = ((rem % m_groups) * CLUSTER + cta_rank) * BLOCK_M;
-            const int n0 = (rem / m_groups) * BLOCK_N;
+            int m0, n0;
+            tile_origin(rem, m0, n0);
             const int kb0 = split * g.kb_per_split;
             const int kb1 = min(g.num_kb, kb0 + g.kb_per_split);
             for (int kb = kb0; kb < kb1; ++kb) {
@@ -524,8 +583,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int q = warp & 3;    // TMEM lane quadrant this warp may access
         const int half = ew >> 2;  // the two warps of a quadrant alternate over column groups
         uint8_t* stg = sStg + ew * Cfg::STG_PER_WARP;
-        const uint64_t seed = (EPI == B200U_EPI_BIAS_DROP_RES) ? load_seed(g.drop) : 0ull;
+        const uint64_t seed = (EPI == B200U_EPI_BIAS_DROP_RES || Cfg::LN) ? load_seed(g.drop) : 0ull;
         const int rr = q * 32 + lane;  // row inside the tile
+        int ln_tiles = 0;              // LN: tiles this CTA has finished (mailbox buffer / barrier parity)
         const int sw = lane & 7;       // 128B-swizzle phase of this row
         int as = 0;
         uint32_t aph = 0;
@@ -534,7 +594,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // tile is being processed, published through one smem slot per accumulator stage
         float bpre[BLOCK_N / 32];
         auto bias_fetch = [&](int tile) {
-            const int bn0 = ((tile % tiles_mn) / m_groups) * BLOCK_N;
+            int bm0, bn0;
+            tile_origin(tile % tiles_mn, bm0, bn0);
 #pragma unroll
             for (int i = 0; i < BLOCK_N / 32; ++i) {
                 const int c = bn0 + lane + 32 * i;
@@ -542,11 +603,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
         };
         if (Cfg::HAS_BIAS && ew == 0 && unit0 < total_tiles) bias_fetch(unit0);
+        if (Cfg::LN && ew == 1) {
+            // this CTA's column tile never changes: gamma / beta slices are staged once (published by the
+            // first tile's epilogue barrier below)
+#pragma unroll
+            for (int i = 0; i < BLOCK_N / 32; ++i) {
+                const int c = ln_rank * BLOCK_N + lane + 32 * i;
+                sGam[lane + 32 * i] = c < g.N ? g.ln_gamma[c] : 0.f;
+                sGam[BLOCK_N + lane + 32 * i] = c < g.N ? g.ln_beta[c] : 0.f;
+            }
+        }
         for (int t = unit0; t < total_tiles; t += unit_stride) {
             const int split = t / tiles_mn;
             const int rem = t - split * tiles_mn;
-            const int m0 = ((rem % m_groups) * CLUSTER + cta_rank) * BLOCK_M;
-            const int n0 = (rem / m_groups) * BLOCK_N;
+            int m0, n0;
+            tile_origin(rem, m0, n0);
             const float* bias_s = sBias + as * BLOCK_N;
             if (Cfg::HAS_BIAS) {
                 if (ew == 0) {
@@ -633,6 +704,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         rpar ^= 1u << gi;
                     }
                     __syncwarp();
+                    uint4 yv[Cfg::LN ? 8 : 1];  // LN: this row's 64 bf16 pre-LayerNorm values stay in registers
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         uint4 rraw = make_uint4(0, 0, 0, 0);
@@ -643,6 +715,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         *reinterpret_cast<uint4*>(dst + lane * 128 + ((j ^ sw) << 4)) = o;
                         if (Cfg::DUAL)
                             *reinterpret_cast<uint4*>(stg + 4096 + lane * 128 + ((j ^ sw) << 4)) = o2;
+                        if (Cfg::LN) yv[Cfg::LN ? j : 0] = o;
                     }
                     tmem_ld_wait();                              // rb = columns col0+32 .. col0+63
                     if (more) tmem_ld_32x32(taddr + gn * 64, ra); else release_acc();
@@ -656,6 +729,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         *reinterpret_cast<uint4*>(dst + lane * 128 + ((j ^ sw) << 4)) = o;
                         if (Cfg::DUAL)
                             *reinterpret_cast<uint4*>(stg + 4096 + lane * 128 + ((j ^ sw) << 4)) = o2;
+                        if (Cfg::LN) yv[Cfg::LN ? j : 0] = o;
                     }
                     fence_proxy_async();
                     __syncwarp();
@@ -670,13 +744,112 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             mbar_arrive(&rempty[prev]);
                         }
                     }
+                    if (EPI == B200U_EPI_MUL && g.colsum) {
+                        // bias gradient of the dense whose output gradient this tile is: column sums of the
+                        // bf16 results over this warp's 32 rows, read back from the swizzled tile (lane c owns
+                        // columns 2c, 2c+1: the 32 lanes cover one 128-byte row, conflict-free), one fp32
+                        // atomic per column and warp. Rows past M are exact zeros (operands zero-filled).
+                        float c0 = 0.f, c1 = 0.f;
+                        const int chunk = lane >> 2, wq = (lane & 3) * 4;
+#pragma unroll 8
+                        for (int r = 0; r < 32; ++r) {
+                            const float2 f = unpack_bf16(*reinterpret_cast<const uint32_t*>(dst + r * 128 + ((chunk ^ (r & 7)) << 4) + wq));
+                            c0 += f.x;
+                            c1 += f.y;
+                        }
+                        const int col = n0 + col0 + 2 * lane;
+                        if (col < g.N) atomicAdd(g.colsum + col, c0);
+                        if (col + 1 < g.N) atomicAdd(g.colsum + col + 1, c1);
+                    }
+                    if (Cfg::LN) {
+                        // ---- fused LayerNorm over the full row (model/layer.py:111-115,152-156) ----
+                        // (1) statistics of this row's 64 bf16-rounded values (the values the backward reads)
+                        float s1 = 0.f;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const uint32_t* w4 = &yv[j].x;
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) { const float2 f = unpack_bf16(w4[k]); s1 += f.x + f.y; }
+                        }
+                        const float mloc = s1 * (1.0f / 64.0f);
+                        float m2 = 0.f;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const uint32_t* w4 = &yv[j].x;
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const float2 f = unpack_bf16(w4[k]);
+                                m2 = fmaf(f.x - mloc, f.x - mloc, m2);
+                                m2 = fmaf(f.y - mloc, f.y - mloc, m2);
+                            }
+                        }
+                        // (2) push (sum, M2) into the mailbox [buffer][this CTA][group][row] of EVERY CTA of the
+                        // cluster with st.async: each store completes 8 transaction bytes on the destination's
+                        // barrier, which one local thread armed with the byte count of the whole exchange
+                        const int buf = ln_tiles & 1;
+                        if (ew == 0 && lane == 0) mbar_arrive_expect_tx(&lnbar[buf], (uint32_t)(g.ln_cl * 2 * BLOCK_M * 8));
+                        const uint32_t mbox = smem_u32(sPart + ((buf * Cfg::LN_MAX_CL + ln_rank) * 2 + gi) * BLOCK_M + rr);
+                        const uint32_t lb = smem_u32(&lnbar[buf]);
+                        for (int r = 0; r < g.ln_cl; ++r)
+                            dsmem_st_async_f32x2(dsmem_addr(mbox, (uint32_t)r), s1, m2, dsmem_addr(lb, (uint32_t)r));
+                        // (3) all 2 * cluster-size partials of the row have landed here: Chan's combination
+                        mbar_wait_cluster(&lnbar[buf], (uint32_t)(ln_tiles >> 1) & 1u);
+                        float tot = 0.f;
+                        const float2* pp = sPart + (size_t)buf * Cfg::LN_MAX_CL * 2 * BLOCK_M + rr;
+                        for (int r = 0; r < 2 * g.ln_cl; ++r) tot += pp[r * BLOCK_M].x;
+                        const float mean = tot / (float)g.N;
+                        float M2 = 0.f;
+                        for (int r = 0; r < 2 * g.ln_cl; ++r) {
+                            const float2 pr = pp[r * BLOCK_M];
+                            const float dm = pr.x * (1.0f / 64.0f) - mean;
+                            M2 += pr.y + 64.0f * dm * dm;
+                        }
+                        const float rstd = rsqrtf(M2 / (float)g.N + g.ln_eps);
+                        if (ln_rank == 0 && gi == 0 && row < g.M) {
+                            if (g.ln_mean) g.ln_mean[row] = mean;
+                            if (g.ln_rstd) g.ln_rstd[row] = rstd;
+                        }
+                        // (4) normalise from registers, write the LayerNorm output over the tile in place (once
+                        // the store of the pre-LN values has finished reading it) and store it through tmC2
+                        if (lane == 0) bulk_wait_read_all();
+                        __syncwarp();
+                        const float* gam = sGam + col0;
+                        const float* bet = sGam + BLOCK_N + col0;
+                        const float nmr = -mean * rstd;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const uint32_t* w4 = &yv[j].x;
+                            const float4 ga0 = *reinterpret_cast<const float4*>(gam + 8 * j);
+                            const float4 ga1 = *reinterpret_cast<const float4*>(gam + 8 * j + 4);
+                            const float4 be0 = *reinterpret_cast<const float4*>(bet + 8 * j);
+                            const float4 be1 = *reinterpret_cast<const float4*>(bet + 8 * j + 4);
+                            const float2 f0 = unpack_bf16(w4[0]), f1 = unpack_bf16(w4[1]);
+                            const float2 f2_ = unpack_bf16(w4[2]), f3 = unpack_bf16(w4[3]);
+                            uint4 ov;
+                            ov.x = pack_bf16(fmaf(fmaf(f0.x, rstd, nmr), ga0.x, be0.x), fmaf(fmaf(f0.y, rstd, nmr), ga0.y, be0.y));
+                            ov.y = pack_bf16(fmaf(fmaf(f1.x, rstd, nmr), ga0.z, be0.z), fmaf(fmaf(f1.y, rstd, nmr), ga0.w, be0.w));
+                            ov.z = pack_bf16(fmaf(fmaf(f2_.x, rstd, nmr), ga1.x, be1.x), fmaf(fmaf(f2_.y, rstd, nmr), ga1.y, be1.y));
+                            ov.w = pack_bf16(fmaf(fmaf(f3.x, rstd, nmr), ga1.z, be1.z), fmaf(fmaf(f3.y, rstd, nmr), ga1.w, be1.w));
+                            *reinterpret_cast<uint4*>(dst + lane * 128 + ((j ^ sw) << 4)) = ov;
+                        }
+                        fence_proxy_async();
+                        __syncwarp();
+                        if (lane == 0) {
+                            tma_store_2d(&tmC2, dst, n0 + col0, m0 + q * 32);
+                            bulk_commit();
+                        }
+                    }
                     prev = gi;
                     gi = gn;
                     have = more;
                 }
-                if (Cfg::HAS_R && prev >= 0 && lane == 0) {
-                    bulk_wait_read_all();  // the last store has finished reading its side-input slot
-                    mbar_arrive(&rempty[prev]);
+                if (Cfg::LN) ++ln_tiles;
+                if (Cfg::HAS_R && prev >= 0) {
+                    __syncwarp();  // (EPI_MUL: every lane's column-sum reads of the slot are done)
+                    if (lane == 0) {
+                        bulk_wait_read_all();  // the last store has finished reading its side-input slot
+                        mbar_arrive(&rempty[prev]);
+                    }
                 }
             }
             if (!released) release_acc();  // warps that had no column group in this tile
@@ -691,6 +864,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     tc_fence_before();
     // no CTA may exit while its peer can still multicast into its smem or arrive on its barriers
+    // (LayerNorm clusters: every push destined to this CTA has been waited for by its epilogue, peers
+    //  never read remote memory, so a CTA may leave as soon as it is done)
     if (CLUSTER > 1) cluster_sync_all(); else __syncthreads();
     if (warp == 2) {
         tc_fence_after();
@@ -790,22 +965,55 @@ static int launch_tc(const b200u_gemm_t* d, GemmArgs& g, cudaStream_t stream) {
     if (rc) return rc;
     tmC2 = tmC;
     tmR = tmC;
-    if (Cfg::DUAL) { rc = make_tmap(&tmC2, d->C2, d->M, d->N, d->ldc2, 32); if (rc) return rc; }
+    if (Cfg::DUAL || Cfg::LN) { rc = make_tmap(&tmC2, d->C2, d->M, d->N, d->ldc2, 32); if (rc) return rc; }
     if (Cfg::HAS_R) { rc = make_tmap(&tmR, d->R, d->M, d->N, d->ldr, BLOCK_M); if (rc) return rc; }
 
     g.m_tiles = (d->M + BLOCK_M - 1) / BLOCK_M;
     g.n_tiles = (d->N + BLOCK_N - 1) / BLOCK_N;
-    const int units = ((g.m_tiles + CLUSTER - 1) / CLUSTER) * g.n_tiles * g.splits;
-    const int max_clusters = num_sms() / CLUSTER;
-    const int grid = (units < max_clusters ? units : max_clusters) * CLUSTER;
+    const int ucl = Cfg::LN ? g.ln_cl : CLUSTER;  // cluster size of the launch
+    const int units = Cfg::LN ? g.m_tiles : ((g.m_tiles + CLUSTER - 1) / CLUSTER) * g.n_tiles * g.splits;
 
     auto kern = gemm_tc_kernel<BLOCK_N, A_MN, B_MN, EPI, CLUSTER>;
-    static bool attr_set = false;  // per template instantiation
-    if (!attr_set) {
-        B200U_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              Cfg::SMEM_BYTES));
-        attr_set = true;
+    // per-device, per-instantiation one-time setup (the attribute is per device; PyTorch calls us from
+    // the main and the autograd thread)
+    static std::mutex mu;
+    static bool attr_set[64] = {};
+    static int ln_max_clusters[64][Cfg::LN_MAX_CL + 1] = {};
+    int dev = 0;
+    B200U_CHECK_CUDA(cudaGetDevice(&dev));
+    B200U_CHECK_ARG(dev >= 0 && dev < 64, "b200u_gemm: device ordinal %d out of range", dev);
+    int max_clusters = num_sms() / ucl;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        if (!attr_set[dev]) {
+            B200U_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                  Cfg::SMEM_BYTES));
+            attr_set[dev] = true;
+        }
+        if (Cfg::LN) {
+            // how many clusters of this size the device can hold at once (GPC boundaries): the persistent
+            // loop must not be sized past it, or the surplus clusters would only start after a full pass
+            if (ln_max_clusters[dev][ucl] == 0) {
+                cudaLaunchConfig_t q = {};
+                q.gridDim = dim3(ucl * (num_sms() / ucl));
+                q.blockDim = dim3(GEMM_THREADS);
+                q.dynamicSmemBytes = Cfg::SMEM_BYTES;
+                cudaLaunchAttribute qa[1];
+                qa[0].id = cudaLaunchAttributeClusterDimension;
+                qa[0].val.clusterDim.x = ucl; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+                q.attrs = qa; q.numAttrs = 1;
+                int n = 0;
+                if (cudaOccupancyMaxActiveClusters(&n, kern, &q) != cudaSuccess || n < 1) {
+                    cudaGetLastError();
+                    n = 1;
+                }
+                ln_max_clusters[dev][ucl] = n;
+            }
+            if (ln_max_clusters[dev][ucl] < max_clusters) max_clusters = ln_max_clusters[dev][ucl];
+        }
     }
+    if (max_clusters < 1) max_clusters = 1;
+    const int grid = (units < max_clusters ? units : max_clusters) * ucl;
     int slot = 0;
     const bool prof = prof_begin(stream, 2.0 * d->M * d->N * d->K, &slot);
     cudaLaunchConfig_t cfg = {};
@@ -815,9 +1023,9 @@ static int launch_tc(const b200u_gemm_t* d, GemmArgs& g, cudaStream_t stream) {
     cfg.stream = stream;
     cudaLaunchAttribute attr[2];
     int na = 0;
-    if (CLUSTER > 1) {
+    if (ucl > 1 || Cfg::LN) {  // (LN with one column tile: an explicit 1-CTA cluster, st.async needs a cluster launch)
         attr[na].id = cudaLaunchAttributeClusterDimension;
-        attr[na].val.clusterDim.x = CLUSTER;
+        attr[na].val.clusterDim.x = ucl;
         attr[na].val.clusterDim.y = 1;
         attr[na].val.clusterDim.z = 1;
         ++na;
@@ -848,20 +1056,34 @@ static int dispatch_bn(const b200u_gemm_t* d, GemmArgs& g, int block_n, cudaStre
     if (d->impl == 1) {
         dim3 grid((d->N + 31) / 32, (d->M + 127) / 128);
         g.splits = 1;
-        launch_k(gemm_simt_kernel<EPI>, dim3(grid), dim3(128), 0, stream, (const bf16*)d->A, d->lda, d->a_mn_major,
+        constexpr int SEPI = EPI == B200U_EPI_BIAS_DROP_RES_LN ? B200U_EPI_BIAS_DROP_RES : EPI;
+        launch_k(gemm_simt_kernel<SEPI>, dim3(grid), dim3(128), 0, stream, (const bf16*)d->A, d->lda, d->a_mn_major,
                                                         (const bf16*)d->B, d->ldb, d->b_mn_major, g);
         B200U_CHECK_LAUNCH("gemm_simt_kernel");
+        if (EPI == B200U_EPI_BIAS_DROP_RES_LN) {
+            B200U_CHECK_ARG(d->ldc == d->N && d->ldc2 == d->N, "b200u_gemm: SIMT LayerNorm epilogue needs dense C / C2");
+            return b200u_layernorm_fwd(d->C, B200U_BF16, d->ln_gamma, d->ln_beta, d->C2, B200U_BF16, d->ln_mean,
+                                       d->ln_rstd, d->M, d->N, d->ln_eps, nullptr, (b200u_stream_t)stream);
+        }
         return B200U_OK;
     }
-    // pairs of vertically adjacent tiles share their B tile through TMA multicast
-    // (measured on B200: multicast at cluster size 2 does not reduce per-SM ingest, so auto = off)
-    const bool pair = d->cluster == 2;
-    if (pair) {
-        if (block_n == 256) return dispatch_major<256, EPI, 2>(d, g, stream);
-        return dispatch_major<128, EPI, 2>(d, g, stream);
+    if constexpr (EPI == B200U_EPI_BIAS_DROP_RES_LN) {
+        // forward-only epilogue: X[M,K] . W[N,K]^T, 128-wide column tiles, one cluster per row block
+        B200U_CHECK_ARG(!d->a_mn_major && !d->b_mn_major, "b200u_gemm: the LayerNorm epilogue needs K-major A and B");
+        return launch_tc<128, false, false, EPI, 1>(d, g, stream);
+    } else {
+        // pairs of vertically adjacent tiles share their B tile through TMA multicast
+        // (measured on B200: multicast at cluster size 2 does not reduce per-SM ingest, so auto = off)
+        const bool pair = d->cluster == 2 && EPI != B200U_EPI_BIAS_GELU_DG && EPI != B200U_EPI_MUL;
+        if constexpr (EPI != B200U_EPI_BIAS_GELU_DG && EPI != B200U_EPI_MUL) {
+            if (pair) {
+                if (block_n == 256) return dispatch_major<256, EPI, 2>(d, g, stream);
+                return dispatch_major<128, EPI, 2>(d, g, stream);
+            }
+        }
+        if (block_n == 256) return dispatch_major<256, EPI, 1>(d, g, stream);
+        return dispatch_major<128, EPI, 1>(d, g, stream);
     }
-    if (block_n == 256) return dispatch_major<256, EPI, 1>(d, g, stream);
-    return dispatch_major<128, EPI, 1>(d, g, stream);
 }
 
 }  // namespace b200u
@@ -893,16 +1115,24 @@ extern "C" int b200u_gemm(const b200u_gemm_t* d, b200u_stream_t stream_) {
     const bool f32_out = d->epilogue == B200U_EPI_ATOMIC_F32 || d->epilogue == B200U_EPI_STORE_F32;
     B200U_CHECK_ARG(d->ldc % (f32_out ? 4 : 8) == 0,
                     "b200u_gemm: ldc alignment (got %d)", d->ldc);
-    if (d->epilogue == B200U_EPI_BIAS_GELU)
+    if (d->epilogue == B200U_EPI_BIAS_GELU || d->epilogue == B200U_EPI_BIAS_GELU_DG)
         B200U_CHECK_ARG(d->C2 && d->bias && d->ldc2 % 8 == 0, "b200u_gemm: BIAS_GELU needs C2 and bias");
+    const bool ln = d->epilogue == B200U_EPI_BIAS_DROP_RES_LN;
+    if (ln) {
+        B200U_CHECK_ARG(d->C2 && d->ldc2 % 8 == 0 && ((uintptr_t)d->C2 & 15) == 0 && d->ln_gamma && d->ln_beta && d->bias,
+                        "b200u_gemm: the LayerNorm epilogue needs C2, bias, ln_gamma and ln_beta");
+        B200U_CHECK_ARG(d->N % 128 == 0 && d->N / 128 <= 8,
+                        "b200u_gemm: the LayerNorm epilogue needs N = 128 * k, k <= 8 (got N=%d)", d->N);
+    }
     if (d->epilogue == B200U_EPI_BIAS_DROP_RES || d->epilogue == B200U_EPI_ADD ||
-        d->epilogue == B200U_EPI_DGELU)
+        d->epilogue == B200U_EPI_DGELU || d->epilogue == B200U_EPI_MUL || ln)
         B200U_CHECK_ARG(d->R && d->ldr % 8 == 0 && ((uintptr_t)d->R & 15) == 0,
                         "b200u_gemm: epilogue %d needs R", d->epilogue);
     B200U_CHECK_ARG(d->splits <= 1 || d->epilogue == B200U_EPI_ATOMIC_F32,
                     "b200u_gemm: split-K requires EPI_ATOMIC_F32");
     B200U_CHECK_ARG(d->block_n == 0 || d->block_n == 128 || d->block_n == 256,
                     "b200u_gemm: block_n must be 0, 128 or 256");
+    B200U_CHECK_ARG(!d->colsum || d->epilogue == B200U_EPI_MUL, "b200u_gemm: colsum is an EPI_MUL output");
 
     GemmArgs g;
     g.M = d->M; g.N = d->N; g.K = d->K;
@@ -910,7 +1140,11 @@ extern "C" int b200u_gemm(const b200u_gemm_t* d, b200u_stream_t stream_) {
     g.bias = d->bias; g.R = (const bf16*)d->R; g.ldr = d->ldr;
     g.drop.seed_ptr = d->drop.seed_ptr;
     g.drop.stream = d->drop.stream;
-    const float p = (d->epilogue == B200U_EPI_BIAS_DROP_RES) ? d->drop.p : 0.f;
+    g.colsum = d->colsum;
+    g.ln_gamma = d->ln_gamma; g.ln_beta = d->ln_beta; g.ln_mean = d->ln_mean; g.ln_rstd = d->ln_rstd;
+    g.ln_eps = d->ln_eps;
+    g.ln_cl = ln ? d->N / 128 : 1;
+    const float p = (d->epilogue == B200U_EPI_BIAS_DROP_RES || ln) ? d->drop.p : 0.f;
     B200U_CHECK_ARG(p >= 0.f && p < 1.f, "b200u_gemm: dropout p out of range");
     g.drop.thresh16 = (uint32_t)(p * 65536.0f + 0.5f);
     g.drop.scale = 1.0f / (1.0f - p);
@@ -954,6 +1188,9 @@ extern "C" int b200u_gemm(const b200u_gemm_t* d, b200u_stream_t stream_) {
         case B200U_EPI_DGELU:         return dispatch_bn<B200U_EPI_DGELU>(d, g, block_n, stream);
         case B200U_EPI_ATOMIC_F32:    return dispatch_bn<B200U_EPI_ATOMIC_F32>(d, g, block_n, stream);
         case B200U_EPI_STORE_F32:     return dispatch_bn<B200U_EPI_STORE_F32>(d, g, block_n, stream);
+        case B200U_EPI_BIAS_GELU_DG:  return dispatch_bn<B200U_EPI_BIAS_GELU_DG>(d, g, block_n, stream);
+        case B200U_EPI_MUL:           return dispatch_bn<B200U_EPI_MUL>(d, g, block_n, stream);
+        case B200U_EPI_BIAS_DROP_RES_LN: return dispatch_bn<B200U_EPI_BIAS_DROP_RES_LN>(d, g, 128, stream);
     }
     return B200U_ERR_ARG;
 }

@@ -2,13 +2,15 @@
 // together the tcgen05 GEMMs, the fused attention and the LayerNorm kernels so the Python side
 // pays one ctypes call per layer and the whole sequence is CUDA-graph capturable.
 //
-// forward (7 launches)                                   reference
+// forward (5 launches)                                   reference
 //   qkv = x0·Wqkvᵀ + bqkv                                layer.py:76-78   (one N=3H GEMM)
 //   ctx = attention(qkv, mask)                           layer.py:80-100
-//   y1  = dropout(ctx·Woᵀ + bo) + x0 ; x1 = LN1(y1)      layer.py:111-115
-//   u   = x1·W1ᵀ + b1 ; g = gelu(u)                      layer.py:139-142
-//   y2  = dropout(g·W2ᵀ + b2) + x1 ; x2 = LN2(y2)        layer.py:152-156
-// backward (12 launches): the exact transposes, weight grads accumulated in fp32 (+=).
+//   y1  = dropout(ctx·Woᵀ + bo) + x0 ; x1 = LN1(y1)      layer.py:111-115 (ONE GEMM: LayerNorm in the epilogue,
+//   u   = x1·W1ᵀ + b1 ; g = gelu(u) ; saves gelu'(u)     layer.py:139-142  row statistics exchanged over DSMEM
+//   y2  = dropout(g·W2ᵀ + b2) + x1 ; x2 = LN2(y2)        layer.py:152-156  by the cluster that owns a row block)
+// (H not a multiple of 128 or > 1024: LayerNorm runs as its own launch, 7 launches.)
+// backward (11 launches): the exact transposes, weight grads accumulated in fp32 (+=); the FFN1 bias
+// gradient is a by-product of the FFN2 dgrad epilogue (du = (dz2·W2) * gelu'(u), column sums folded in).
 #include "../../include/b200u.h"
 #include "common.cuh"
 
@@ -31,11 +33,21 @@ b200u_dropout_t site(const b200u_layer_params_t* p, int which, float prob) {
     return d;
 }
 
+struct LnArgs {
+    const float* gamma; const float* beta; float* mean; float* rstd; float eps;
+};
+
 int gemm(int M, int N, int K, const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn,
          int epi, void* C, int ldc, void* C2, int ldc2, const float* bias, const void* R, int ldr,
-         const b200u_dropout_t* drop, int impl, cudaStream_t stream) {
+         const b200u_dropout_t* drop, int impl, cudaStream_t stream, float* colsum = nullptr,
+         const LnArgs* ln = nullptr) {
     b200u_gemm_t g;
     memset(&g, 0, sizeof(g));
+    g.colsum = colsum;
+    if (ln) {
+        g.ln_gamma = ln->gamma; g.ln_beta = ln->beta; g.ln_mean = ln->mean; g.ln_rstd = ln->rstd;
+        g.ln_eps = ln->eps;
+    }
     g.M = M; g.N = N; g.K = K;
     g.A = A; g.lda = lda; g.a_mn_major = a_mn;
     g.B = B; g.ldb = ldb; g.b_mn_major = b_mn;
@@ -72,6 +84,12 @@ struct SideCtx {
 };
 // b200u_set_bwd_streams(): 1 = weight gradients on the side stream, 0 = single stream
 // (the environment variable B200U_BWD_STREAMS=0 selects the single-stream order at load time)
+// b200u_set_fused_layernorm(): 1 (default) = LayerNorm inside the attn-out / FFN2 GEMM epilogues
+// (B200U_FUSE_LN=0 selects the separate launches at load time)
+int g_fuse_ln = [] {
+    const char* e = getenv("B200U_FUSE_LN");
+    return (e && e[0] == '0') ? 0 : 1;
+}();
 int g_side_mode = [] {
     const char* e = getenv("B200U_BWD_STREAMS");
     return (e && e[0] == '0') ? 0 : 1;
@@ -99,6 +117,11 @@ SideCtx* side_ctx() {
 
 }  // namespace
 
+extern "C" int b200u_set_fused_layernorm(int on) {
+    g_fuse_ln = on ? 1 : 0;
+    return B200U_OK;
+}
+
 extern "C" int b200u_set_bwd_streams(int two_streams) {
     g_side_mode = two_streams ? 1 : 0;
     return B200U_OK;
@@ -118,16 +141,30 @@ extern "C" int b200u_bert_layer_fwd(const b200u_layer_params_t* p, const void* x
     TRY(gemm(M, 3 * H, H, x0, H, 0, p->Wqkv, H, 0, B200U_EPI_STORE, s->qkv, 3 * H, nullptr, 0, p->bqkv,
              nullptr, 0, nullptr, p->gemm_impl, st));
     TRY(b200u_attention_fwd(s->qkv, p->mask, s->ctx, s->lse, p->B, p->L, p->heads, H, &d_attn, st));
-    TRY(gemm(M, H, H, s->ctx, H, 0, p->Wo, H, 0, B200U_EPI_BIAS_DROP_RES, s->y1, H, nullptr, 0, p->bo, x0,
-             H, &d_h1, p->gemm_impl, st));
-    TRY(b200u_layernorm_fwd(s->y1, B200U_BF16, p->ln1_g, p->ln1_b, s->x1, B200U_BF16, s->mean1, s->rstd1,
-                            M, H, p->eps, nullptr, st));
-    TRY(gemm(M, I, H, s->x1, H, 0, p->W1, H, 0, B200U_EPI_BIAS_GELU, s->u, I, s->g, I, p->b1, nullptr, 0,
+    const bool fuse_ln = g_fuse_ln && (H % 128 == 0) && (H / 128 <= 8);
+    if (fuse_ln) {
+        const LnArgs ln1 = {p->ln1_g, p->ln1_b, s->mean1, s->rstd1, p->eps};
+        TRY(gemm(M, H, H, s->ctx, H, 0, p->Wo, H, 0, B200U_EPI_BIAS_DROP_RES_LN, s->y1, H, s->x1, H, p->bo, x0, H,
+                 &d_h1, p->gemm_impl, st, nullptr, &ln1));
+    } else {
+        TRY(gemm(M, H, H, s->ctx, H, 0, p->Wo, H, 0, B200U_EPI_BIAS_DROP_RES, s->y1, H, nullptr, 0, p->bo, x0,
+                 H, &d_h1, p->gemm_impl, st));
+        TRY(b200u_layernorm_fwd(s->y1, B200U_BF16, p->ln1_g, p->ln1_b, s->x1, B200U_BF16, s->mean1, s->rstd1,
+                                M, H, p->eps, nullptr, st));
+    }
+    // saved->u holds gelu'(u) (what the backward needs), saved->g = gelu(u)
+    TRY(gemm(M, I, H, s->x1, H, 0, p->W1, H, 0, B200U_EPI_BIAS_GELU_DG, s->u, I, s->g, I, p->b1, nullptr, 0,
              nullptr, p->gemm_impl, st));
-    TRY(gemm(M, H, I, s->g, I, 0, p->W2, I, 0, B200U_EPI_BIAS_DROP_RES, s->y2, H, nullptr, 0, p->b2, s->x1,
-             H, &d_h2, p->gemm_impl, st));
-    TRY(b200u_layernorm_fwd(s->y2, B200U_BF16, p->ln2_g, p->ln2_b, x2, B200U_BF16, s->mean2, s->rstd2, M,
-                            H, p->eps, nullptr, st));
+    if (fuse_ln) {
+        const LnArgs ln2 = {p->ln2_g, p->ln2_b, s->mean2, s->rstd2, p->eps};
+        TRY(gemm(M, H, I, s->g, I, 0, p->W2, I, 0, B200U_EPI_BIAS_DROP_RES_LN, s->y2, H, x2, H, p->b2, s->x1, H,
+                 &d_h2, p->gemm_impl, st, nullptr, &ln2));
+    } else {
+        TRY(gemm(M, H, I, s->g, I, 0, p->W2, I, 0, B200U_EPI_BIAS_DROP_RES, s->y2, H, nullptr, 0, p->b2, s->x1,
+                 H, &d_h2, p->gemm_impl, st));
+        TRY(b200u_layernorm_fwd(s->y2, B200U_BF16, p->ln2_g, p->ln2_b, x2, B200U_BF16, s->mean2, s->rstd2, M,
+                                H, p->eps, nullptr, st));
+    }
     return B200U_OK;
 }
 
@@ -160,16 +197,16 @@ extern "C" int b200u_bert_layer_bwd(const b200u_layer_params_t* p, const void* x
     TRY(b200u_layernorm_bwd(dx2, s->y2, B200U_BF16, s->mean2, s->rstd2, p->ln2_g, w->dres,
                             p->p_hidden > 0.f ? w->dz : nullptr, g->dln2_g, g->dln2_b, g->db2, M, H, &d_h2,
                             0, st));
-    // FFN2: dW2[H,I] += dz2ᵀ·g (side) ; du = (dz2·W2) * gelu'(u)
+    // FFN2: dW2[H,I] += dz2ᵀ·g (side) ; du = (dz2·W2) * gelu'(u) with gelu'(u) saved by the forward, and
+    // db1 += colsum(du) folded into the same epilogue
     FORK(0);
     TRY(gemm(H, I, M, dz2, H, 1, s->g, I, 1, B200U_EPI_ATOMIC_F32, g->dW2, I, nullptr, 0, nullptr, nullptr,
              0, nullptr, impl, sd));
     if (sc) B200U_CHECK_CUDA(cudaEventRecord(sc->w2_done, sd));
-    TRY(gemm(M, I, H, dz2, H, 0, p->W2, I, 1, B200U_EPI_DGELU, w->du, I, nullptr, 0, nullptr, s->u, I,
-             nullptr, impl, st));
-    // FFN1: db1 += colsum(du), dW1[I,H] += duᵀ·x1 (side) ; dx1 = du·W1 + dres
+    TRY(gemm(M, I, H, dz2, H, 0, p->W2, I, 1, B200U_EPI_MUL, w->du, I, nullptr, 0, nullptr, s->u, I,
+             nullptr, impl, st, g->db1));
+    // FFN1: dW1[I,H] += duᵀ·x1 (side) ; dx1 = du·W1 + dres
     FORK(1);
-    TRY(b200u_colsum_accum(w->du, I, g->db1, M, I, sd));
     TRY(gemm(I, H, M, w->du, I, 1, s->x1, H, 1, B200U_EPI_ATOMIC_F32, g->dW1, H, nullptr, 0, nullptr,
              nullptr, 0, nullptr, impl, sd));
     TRY(gemm(M, H, I, w->du, I, 0, p->W1, H, 1, B200U_EPI_ADD, w->dx1, H, nullptr, 0, nullptr, w->dres, H,

@@ -8,8 +8,8 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import (EPI_ADD, EPI_ATOMIC_F32, EPI_BIAS_DROP_RES, EPI_BIAS_GELU, EPI_DGELU, EPI_STORE,
-                   EPI_STORE_F32)
+from ._lib import (EPI_ADD, EPI_ATOMIC_F32, EPI_BIAS_DROP_RES, EPI_BIAS_DROP_RES_LN, EPI_BIAS_GELU,
+                   EPI_BIAS_GELU_DG, EPI_DGELU, EPI_DUAL, EPI_MUL, EPI_STORE, EPI_STORE_F32)
 
 
 def _ld(t):
@@ -18,10 +18,13 @@ def _ld(t):
 
 
 def gemm(a, b, *, a_mn=False, b_mn=False, epilogue=EPI_STORE, out=None, out2=None, bias=None,
-         res=None, drop=None, splits=0, block_n=0, impl=0, cluster=0):
+         res=None, drop=None, splits=0, block_n=0, impl=0, cluster=0, colsum=None, ln=None):
     """acc[M,N] = sum_k A(m,k) B(n,k) with a fused epilogue (see include/b200u.h, K3).
 
     a: [M,K] (or [K,M] when a_mn), b: [N,K] (or [K,N] when b_mn); bf16, row-major.
+    colsum (EPI_MUL): f32 [N], += column sums of the output. ln (EPI_BIAS_DROP_RES_LN): tuple
+    (gamma f32 [N], beta f32 [N], eps, mean f32 [M] or None, rstd f32 [M] or None); out = pre-LayerNorm
+    values, out2 = LayerNorm output. Dual-output epilogues return (out, out2).
     """
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
     M, K = (a.shape[1], a.shape[0]) if a_mn else (a.shape[0], a.shape[1])
@@ -32,7 +35,7 @@ def gemm(a, b, *, a_mn=False, b_mn=False, epilogue=EPI_STORE, out=None, out2=Non
         assert epilogue != EPI_ATOMIC_F32, "EPI_ATOMIC_F32 accumulates into an existing buffer"
         out = torch.empty(M, N, device=a.device, dtype=torch.float32 if f32_out else torch.bfloat16)
     assert out.dtype == (torch.float32 if f32_out else torch.bfloat16) and tuple(out.shape) == (M, N)
-    if epilogue == EPI_BIAS_GELU and out2 is None:
+    if epilogue in EPI_DUAL and out2 is None:
         out2 = torch.empty(M, N, device=a.device, dtype=torch.bfloat16)
     g = _lib.GemmT()
     g.M, g.N, g.K = M, N, K
@@ -51,8 +54,19 @@ def gemm(a, b, *, a_mn=False, b_mn=False, epilogue=EPI_STORE, out=None, out2=Non
     if drop is not None:
         g.drop = drop
     g.splits, g.block_n, g.impl, g.cluster = splits, block_n, impl, cluster
+    if colsum is not None:
+        assert colsum.dtype == torch.float32 and colsum.numel() == N and colsum.is_contiguous()
+        g.colsum = colsum.data_ptr()
+    if ln is not None:
+        gamma, beta, eps, mean, rstd = ln
+        assert gamma.dtype == torch.float32 and beta.dtype == torch.float32 and gamma.numel() == N == beta.numel()
+        g.ln_gamma, g.ln_beta, g.ln_eps = gamma.data_ptr(), beta.data_ptr(), float(eps)
+        for t in (mean, rstd):
+            assert t is None or (t.dtype == torch.float32 and t.numel() == M and t.is_contiguous())
+        g.ln_mean = mean.data_ptr() if mean is not None else None
+        g.ln_rstd = rstd.data_ptr() if rstd is not None else None
     _lib.check(_lib.lib().b200u_gemm(C.byref(g), _lib.stream_ptr()), "b200u_gemm")
-    return (out, out2) if epilogue == EPI_BIAS_GELU else out
+    return (out, out2) if epilogue in EPI_DUAL else out
 
 
 # --------------------------------------------------------------------------------------------

@@ -78,6 +78,86 @@ def test_gemm_epilogues_and_splitk():
     assert (o0 - o1).abs().max() <= 1e-3 * ref.abs().max()
 
 
+def test_gemm_gelu_derivative_and_mul_colsum_epilogues():
+    """EPI_BIAS_GELU_DG saves gelu'(u) next to gelu(u) (model/layer.py:139-142 forward) and EPI_MUL consumes it
+    in the backward with the bias-gradient column sums folded into the same epilogue."""
+    _require_gpu()
+    from meme_challenge_b200 import _lib, ops
+    M, N, K = 520, 384, 320
+    torch.manual_seed(12)
+    a = torch.randn(M, K, device=DEV).bfloat16()
+    b = (torch.randn(N, K, device=DEV) * 0.1).bfloat16()
+    bias = torch.randn(N, device=DEV) * 0.5
+    u_ref = (a.float().cpu() @ b.float().cpu().t() + bias.cpu()).bfloat16().float()   # the kernel rounds u to bf16 first
+    x = u_ref.clone().requires_grad_(True)
+    gval = O.gelu(x)
+    gval.sum().backward()
+    for impl in (0, 1):
+        for bn in (128, 256):
+            dg, gv = ops.gemm(a, b, bias=bias, epilogue=_lib.EPI_BIAS_GELU_DG, block_n=bn, impl=impl)
+            # u itself may differ by one bf16 ulp between accumulation orders: compare through smooth functions
+            assert (gv.float().cpu() - gval.detach()).abs().max() <= 2e-2 * gval.abs().max()
+            assert (dg.float().cpu() - x.grad).abs().max() <= 2e-2
+    # backward epilogue: out = acc * R, colsum += column sums of the bf16 output
+    r = torch.rand(M, N, device=DEV).bfloat16()
+    ref = (a.float().cpu() @ b.float().cpu().t()) * r.float().cpu()
+    for impl in (0, 1):
+        for bn in (128, 256):
+            cs = torch.full((N,), 3.0, device=DEV)
+            out = ops.gemm(a, b, res=r, epilogue=_lib.EPI_MUL, colsum=cs, block_n=bn, impl=impl)
+            assert (out.float().cpu() - ref).abs().max() <= 1e-2 * ref.abs().max()
+            want = out.float().sum(0).cpu() + 3.0
+            assert (cs.cpu() - want).abs().max() <= 1e-3 * want.abs().max() + 1e-3
+    # B stored [K, N] (the dgrad layout the BertLayer backward uses)
+    bt = b.t().contiguous()
+    cs = torch.zeros(N, device=DEV)
+    out = ops.gemm(a, bt, b_mn=True, res=r, epilogue=_lib.EPI_MUL, colsum=cs)
+    assert (out.float().cpu() - ref).abs().max() <= 1e-2 * ref.abs().max()
+    assert (cs.cpu() - out.float().sum(0).cpu()).abs().max() <= 1e-3 * out.float().sum(0).abs().max().cpu() + 1e-3
+
+
+@pytest.mark.parametrize("N", [128, 768, 1024])
+@pytest.mark.parametrize("M", [100, 2624])
+def test_gemm_fused_layernorm_epilogue(M, N):
+    """EPI_BIAS_DROP_RES_LN: y = acc + bias + R (bf16) and LayerNorm(y) over the full row from ONE launch, the
+    row statistics exchanged between the N/128 CTAs of a cluster (model/layer.py:111-115,152-156)."""
+    _require_gpu()
+    from meme_challenge_b200 import _lib, ops
+    K = 320
+    torch.manual_seed(13)
+    a = torch.randn(M, K, device=DEV).bfloat16()
+    b = (torch.randn(N, K, device=DEV) * 0.1).bfloat16()
+    bias = torch.randn(N, device=DEV) * 0.5
+    res = (torch.randn(M, N, device=DEV) * 2 + 0.3).bfloat16()
+    gamma = torch.randn(N, device=DEV) * 0.3 + 1
+    beta = torch.randn(N, device=DEV) * 0.1
+    mean = torch.empty(M, device=DEV)
+    rstd = torch.empty(M, device=DEV)
+    y, x = ops.gemm(a, b, bias=bias, res=res, epilogue=_lib.EPI_BIAS_DROP_RES_LN,
+                    ln=(gamma, beta, 1e-12, mean, rstd))
+    y_ref = a.float().cpu() @ b.float().cpu().t() + bias.cpu() + res.float().cpu()
+    assert (y.float().cpu() - y_ref).abs().max() <= 1e-2 * y_ref.abs().max()
+    # LayerNorm of the bf16 values the kernel stored (what the standalone kernel and the backward see)
+    yb = y.float().cpu()
+    x_ref = torch.nn.functional.layer_norm(yb, (N,), gamma.cpu(), beta.cpu(), 1e-12)
+    assert (x.float().cpu() - x_ref).abs().max() <= 2e-2
+    assert (mean.cpu() - yb.mean(1)).abs().max() <= 1e-4
+    rs = 1.0 / torch.sqrt(yb.var(1, unbiased=False) + 1e-12)
+    assert ((rstd.cpu() - rs).abs() / rs).max() <= 1e-4
+    # identical to the separate launches (GEMM + standalone LayerNorm) up to fp32 summation order
+    y2 = ops.gemm(a, b, bias=bias, res=res, epilogue=_lib.EPI_BIAS_DROP_RES)
+    assert torch.equal(y2, y)
+    x2, mean2, rstd2 = ops.layernorm_fwd(y2, gamma, beta, 1e-12)
+    assert (x2.float() - x.float()).abs().max().item() <= 2e-2
+    assert (mean2 - mean).abs().max().item() <= 1e-5 and ((rstd2 - rstd).abs() / rstd2).max().item() <= 1e-5
+    # dropout inside the fused epilogue draws the same mask as the unfused one (same counter stream)
+    seed = torch.tensor([5], device=DEV, dtype=torch.int64)
+    d = _lib.dropout_t(seed, 9, 0.1)
+    yd, _ = ops.gemm(a, b, bias=bias, res=res, epilogue=_lib.EPI_BIAS_DROP_RES_LN, drop=d, ln=(gamma, beta, 1e-12, None, None))
+    yd2 = ops.gemm(a, b, bias=bias, res=res, epilogue=_lib.EPI_BIAS_DROP_RES, drop=d)
+    assert torch.equal(yd, yd2)
+
+
 def test_gemm_dropout_statistics():
     _require_gpu()
     from meme_challenge_b200 import _lib, ops
