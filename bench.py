@@ -221,7 +221,7 @@ def run_b200(args, rank, world, local_rank):
     from meme_challenge_b200.model.meme_uniter import MemeUniter
     from meme_challenge_b200.model.model import UniterConfig, UniterModel
     from meme_challenge_b200.train import TrainStep
-    from oracle import uniter_oracle as O  # synthetic batch generator only (test infrastructure)
+    from meme_challenge_b200.data.synthetic import synth_batch
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -242,13 +242,14 @@ def run_b200(args, rank, world, local_rank):
     if world == 1:
         dp_modes = ["eager"] if args.no_graph else ["graph", "eager"]
     ts = TrainStep(model, lr=3e-5, weight_decay=1e-3, gradient_accumulation=ACCUM, max_grad_norm=5.0, pos_wt=1.8,
-                   overlap_comm=True, comm_sm_reserve=args.comm_sm_reserve if world > 1 else 0)
+                   overlap_comm=True, comm_sm_reserve=args.comm_sm_reserve if world > 1 else 0,
+                   fuse_window=(args.window == "fused"))
 
     # synthetic data: a ring of distinct host batches (pinned) and their device copies
     n_sets = 4
     host, devb = [], []
     for i in range(n_sets * ACCUM):
-        b = O.synth_batch(B, T, R, seed=1234 + rank * 1000 + i)
+        b = synth_batch(B, T, R, seed=1234 + rank * 1000 + i)
         hb = {k: v.pin_memory() for k, v in b.items() if torch.is_tensor(v)}
         hb["labels"] = b["labels"].float().pin_memory()
         host.append(hb)
@@ -398,6 +399,7 @@ def run_b200(args, rank, world, local_rank):
                 "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "global_batch": B * world, "grad_accum": ACCUM,
                            "memes_per_step": ACCUM * B * world, "parallelism": "dp%d" % world,
+                           "window": args.window,
                            "cuda_graph": use_graph, "dp_mode": dp_mode if world > 1 else None,
                            "nccl_max_ctas": args.nccl_max_ctas if world > 1 else None,
                            "comm_sm_reserve": args.comm_sm_reserve if world > 1 else None,
@@ -431,6 +433,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--window", default="pipelined", choices=["pipelined", "fused"],
+                    help="how the micro-batches of one accumulation window are executed: pipelined = one "
+                         "forward/backward per micro-batch (forward i+1 beside backward i); fused = one pass over "
+                         "all accum x 16 memes (same gradients and per-micro-batch losses, see TrainStep.fuse_batches)")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--dp-mode", default="auto", choices=["auto", "graph-overlap", "graph", "eager"],
                     help="N > 1: how the data-parallel step is launched (auto = first mode that captures)")

@@ -454,14 +454,19 @@ class LayerNormFn(torch.autograd.Function):
         return dx.to(x.dtype), None, None, None
 
 
-def bce_with_logits(logits, labels, pos_weight=1.0, grad_scale=1.0, want_grad=True):
+def bce_with_logits(logits, labels, pos_weight=1.0, grad_scale=1.0, want_grad=True, dl_out=None):
     """Fused BCEWithLogitsLoss(pos_weight) mean loss, its gradient and sigmoid probabilities
-    (train_template.py:64-65,98-99,117-118) in one launch. Returns (loss[1], dlogits[B], probs[B])."""
+    (train_template.py:64-65,98-99,117-118) in one launch. Returns (loss[1], dlogits[B], probs[B]).
+    dl_out: optional contiguous f32 [B] destination for the gradient (a slice of a larger buffer)."""
     x = logits.reshape(-1).contiguous().float()
     y = labels.reshape(-1).contiguous().float()
     B = x.numel()
     loss = torch.empty(1, device=x.device, dtype=torch.float32)
-    dl = torch.empty(B, device=x.device, dtype=torch.float32) if want_grad else None
+    if dl_out is not None:
+        assert dl_out.dtype == torch.float32 and dl_out.numel() == B and dl_out.is_contiguous()
+        dl = dl_out
+    else:
+        dl = torch.empty(B, device=x.device, dtype=torch.float32) if want_grad else None
     probs = torch.empty(B, device=x.device, dtype=torch.float32)
     ops._call("b200u_bce_logits", P(x), P(y), float(pos_weight), float(grad_scale), P(loss), P(dl), P(probs), B)
     return loss, dl, probs

@@ -83,7 +83,7 @@ class GradBuckets(object):
 class TrainStep(object):
     def __init__(self, model, lr=3e-5, weight_decay=1e-3, betas=(0.9, 0.999), eps=1e-8,
                  gradient_accumulation=2, max_grad_norm=5.0, pos_wt=1.8, process_group=None,
-                 overlap_comm=True, comm_sm_reserve=0):
+                 overlap_comm=True, comm_sm_reserve=0, fuse_window=False):
         self.model = model
         self.um = model.uniter_model
         self.accum = int(gradient_accumulation)
@@ -101,6 +101,10 @@ class TrainStep(object):
         # software-pipeline the micro-batches of a window over two streams (see step()); B200U_PIPELINE=0 disables
         self.pipeline = os.environ.get("B200U_PIPELINE", "1") != "0"
         self._aux_stream = None
+        # fuse_window: run the micro-batches of one accumulation window as ONE forward/backward pass over
+        # accum * B samples (see _step_fused): same gradients, half the launches, twice the rows per GEMM
+        self.fuse_window = bool(fuse_window)
+        self._static_cat = None
 
         # one flat store for the whole MemeUniter (UNITER + classification head)
         store = FlatStore(model)
@@ -251,6 +255,67 @@ class TrainStep(object):
     def micro_step(self, batch, last, first=True):
         return self._backward(self._forward_loss(batch, last, first))
 
+    # ------------------------------------------------------------------ fused accumulation window
+    @staticmethod
+    def fuse_batches(batches):
+        """Concatenate the micro-batches of one accumulation window along the batch dimension.
+
+        Samples are independent in forward and backward (no cross-sample op on the path), so the window's
+        gradient sum_i grad(mean-loss of micro-batch i) can be produced by one pass over all samples.
+        Micro-batches padded to different widths are right-padded to the widest: attention-mask columns
+        with 0 (never attended), gather-index columns with the identity tail the reference's
+        get_gather_index produces for padded positions (utils/utils.py:113), region rows with zeros."""
+        L = max(b["attn_mask"].shape[1] for b in batches)
+        R = max(b["img_feat"].shape[1] for b in batches)
+        out = {}
+        for k in ("input_ids", "position_ids", "img_feat", "img_pos_feat", "attn_mask", "gather_index", "labels"):
+            parts = []
+            for b in batches:
+                t = b[k]
+                if k in ("img_feat", "img_pos_feat") and t.shape[1] < R:
+                    t = torch.cat([t, t.new_zeros(t.shape[0], R - t.shape[1], t.shape[2])], 1)
+                elif k == "attn_mask" and t.shape[1] < L:
+                    t = torch.cat([t, t.new_zeros(t.shape[0], L - t.shape[1])], 1)
+                elif k == "gather_index" and t.shape[1] < L:
+                    tail = torch.arange(t.shape[1], L, device=t.device, dtype=t.dtype).unsqueeze(0)
+                    t = torch.cat([t, tail.expand(t.shape[0], -1)], 1)
+                parts.append(t)
+            out[k] = torch.cat(parts, 0)
+        return out
+
+    def _step_fused(self, batches, cat=None):
+        """All micro-batches of the window in one pass. Per-micro-batch mean losses (and their gradients)
+        are formed on the slices of the joint logits, so the accumulated gradient, the 1/accum averaging
+        and the reported losses are those of the sequential window (train_template.py:95-103)."""
+        if cat is None:
+            cat = self.fuse_batches(batches)
+        sizes = [b["labels"].shape[0] for b in batches]
+        kw = dict(input_ids=cat["input_ids"], position_ids=cat["position_ids"], img_feat=cat["img_feat"],
+                  img_pos_feat=cat["img_pos_feat"], attention_mask=cat["attn_mask"],
+                  gather_index=cat["gather_index"], output_all_encoded_layers=False)
+        comm = self.world > 1
+        self.um._layer_grad_ready_cb = self._on_layer_done if (comm and self.overlap_comm) else None
+        sparse = (comm and self.overlap_comm and self.sparse_word and self.word_slice is not None)
+        if sparse:
+            self._word_rows = []
+        self.um._sparse_word_cb = self._on_word_rows if sparse else None
+        try:
+            logits = self.model(**kw)
+        finally:
+            self.um._layer_grad_ready_cb = None
+            self.um._sparse_word_cb = None
+        flat_logits = logits.reshape(-1)
+        dl = torch.empty_like(flat_logits, dtype=torch.float32)
+        outs, o = [], 0
+        for n in sizes:
+            loss, _, probs = F_.bce_with_logits(flat_logits[o:o + n], cat["labels"][o:o + n], self.pos_wt,
+                                                dl_out=dl[o:o + n])
+            outs.append((loss, probs))
+            o += n
+        state = (logits, dl, None, None, comm, sparse, True)
+        self._backward(state)
+        return outs
+
     # ------------------------------------------------------------------ optimizer
     def optimizer_step(self):
         self.comm.wait()
@@ -279,9 +344,13 @@ class TrainStep(object):
         SMs idle in their launch / first-load / epilogue-drain phases; two chains fill each other's
         gaps). Backward passes stay ordered (they share scratch buffers and, with world_size > 1, the
         last one triggers the bucket all-reduces), forwards stay ordered (dropout seed sequence)."""
-        assert len(batches) == self.accum
+        # (the reference's first optimizer step fires after ONE micro-batch and still divides by the
+        #  accumulation count, train_template.py:101-103: a shorter window is allowed, the scale is not changed)
+        assert 1 <= len(batches) <= self.accum
         n = len(batches)
-        if n == 1 or not self.pipeline:
+        if self.fuse_window and n > 1:
+            outs = self._step_fused(batches, self._static_cat if batches is self._static else None)
+        elif n == 1 or not self.pipeline:
             outs = [self.micro_step(b, last=(i == n - 1), first=(i == 0)) for i, b in enumerate(batches)]
         else:
             main = torch.cuda.current_stream()
@@ -326,7 +395,21 @@ class TrainStep(object):
         backward hooks fork onto the process group's stream inside the capture and `wait()` joins
         them before the optimizer nodes, so the replayed graph keeps the comm/backward overlap.
         (thread_local capture mode: the NCCL watchdog thread may poll events while we capture.)"""
-        static = [{k: v.clone() for k, v in b.items() if torch.is_tensor(v)} for b in example_batches]
+        if self.fuse_window and len(example_batches) > 1:
+            # the static micro-batch buffers are views of one concatenated set: refreshing them fills the
+            # fused batch in place (micro-batches of one captured window share their padded widths)
+            ex = [{k: v for k, v in b.items() if torch.is_tensor(v)} for b in example_batches]
+            cat = self.fuse_batches(ex)
+            static, o = [], 0
+            for b in ex:
+                n = b["labels"].shape[0]
+                static.append({k: v[o:o + n] for k, v in cat.items()})
+                o += n
+            self._static_cat = cat
+        else:
+            static = [{k: v.clone() for k, v in b.items() if torch.is_tensor(v)} for b in example_batches]
+            self._static_cat = None
+        self._static = static
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):

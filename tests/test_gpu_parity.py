@@ -609,6 +609,69 @@ def test_pipelined_window_equals_sequential_window():
             assert _cos(got_p[n] - 0, ref_p[n] - 0) > 0.999999, (graph, n)
 
 
+def test_fused_window_equals_sequential_window():
+    """TrainStep(fuse_window=True) runs the micro-batches of an accumulation window as ONE pass over all their
+    samples (ragged micro-batches padded to a common width with masked columns / identity gather tail): the
+    per-micro-batch losses and the parameters after two optimizer steps must equal the sequential window's,
+    eagerly and through CUDA-graph replay. Also the reference's first-step quirk (train_template.py:101-103):
+    a window of ONE micro-batch still divides by the accumulation count."""
+    _require_gpu()
+    from meme_challenge_b200.train import TrainStep
+    cfg = dict(TINY)
+    cfg["hidden_dropout_prob"] = 0.0
+    cfg["attention_probs_dropout_prob"] = 0.0
+
+    def batches(step, variable):
+        out = []
+        for i in range(2):
+            b = O.synth_batch(4, 12, 10, seed=80 + 2 * step + i, variable=variable, img_dim=IMG_DIM,
+                              vocab=TINY["vocab_size"], min_txt=2, min_bb=2)
+            d = {k: v.to(DEV) for k, v in b.items() if torch.is_tensor(v)}
+            d["labels"] = b["labels"].float().to(DEV)
+            out.append(d)
+        return out
+
+    def run(fuse, graph, variable):
+        m = _build(cfg, IMG_DIM, seed=3).train()
+        ts = TrainStep(m, lr=1e-3, weight_decay=1e-3, gradient_accumulation=2, max_grad_norm=5.0, pos_wt=1.8,
+                       fuse_window=fuse)
+        ts.pipeline = False
+        losses = []
+        if graph:
+            ts.capture(batches(0, variable), warmup=0)
+            for step in range(2):
+                ts.load_static(batches(step, variable))
+                outs = ts.replay()
+                losses.append([float(o[0].item()) for o in outs])
+        else:
+            for step in range(2):
+                outs = ts.step(batches(step, variable))
+                losses.append([float(o[0].item()) for o in outs])
+        torch.cuda.synchronize()
+        return {n: p.detach().clone() for n, p in m.named_parameters()}, losses
+
+    for variable, graph in ((True, False), (False, False), (False, True)):
+        ref_p, ref_l = run(False, False, variable)
+        got_p, got_l = run(True, graph, variable)
+        assert np.allclose(np.array(got_l), np.array(ref_l), rtol=1e-4, atol=1e-5), (variable, graph, got_l, ref_l)
+        for n in ref_p:
+            assert (got_p[n] - ref_p[n]).abs().max() <= 2e-4, (variable, graph, n)
+            assert _cos(got_p[n] - 0, ref_p[n] - 0) > 0.999999, (variable, graph, n)
+
+    # first-step quirk: one micro-batch, gradient still divided by accum = 2
+    m = _build(cfg, IMG_DIM, seed=3).train()
+    ts = TrainStep(m, lr=1e-3, weight_decay=0.0, gradient_accumulation=2, max_grad_norm=1e9, pos_wt=1.8)
+    b0 = batches(0, True)[:1]
+    logits = m(**_kw(b0[0]))
+    loss = torch.nn.BCEWithLogitsLoss(pos_weight=torch.tensor([1.8], device=DEV))(logits.squeeze(1), b0[0]["labels"])
+    m.zero_grad()
+    loss.backward()
+    want = torch.cat([p.grad.flatten() for p in m.parameters() if p.grad is not None]).norm().item() / 2.0
+    m.zero_grad()
+    ts.step(b0)
+    assert abs(ts.gnorm.item() - want) <= 1e-3 * want
+
+
 # ----------------------------------------------------------------------------------------------
 # optimal transport (model/ot.py): golden vectors from the unmodified reference + oracle
 # ----------------------------------------------------------------------------------------------

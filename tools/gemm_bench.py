@@ -7,7 +7,7 @@ from meme_challenge_b200 import _lib, ops
 
 dev = "cuda"
 E = _lib
-M, H, I = 2624, 768, 3072
+M, H, I = int(os.environ.get("GB_M", "2624")), 768, 3072
 if len(sys.argv) > 1 and sys.argv[1] == "large":
     H, I = 1024, 4096
 seed = torch.tensor([7], device=dev, dtype=torch.int64)
@@ -61,3 +61,14 @@ timeit("ffn2_dgrad MUL + colsum (fused)", lambda i: ops.gemm(*ab[i], b_mn=True, 
 ab = mk(M, 3 * H, H)
 timeit("qkv_fwd STORE bn=256", lambda i: ops.gemm(*ab[i], bias=torch.zeros(3 * H, device=dev), epilogue=E.EPI_STORE, block_n=256), 2.0 * M * 3 * H * H)
 timeit("qkv_fwd STORE bn=128", lambda i: ops.gemm(*ab[i], bias=torch.zeros(3 * H, device=dev), epilogue=E.EPI_STORE, block_n=128), 2.0 * M * 3 * H * H)
+# remaining shapes of the layer (backward)
+ab = mk(M, H, I, 0, 1)
+timeit("ffn1_dgrad ADD", lambda i: ops.gemm(*ab[i], b_mn=True, res=res_h, epilogue=E.EPI_ADD, out=out_h), 2.0 * M * H * I)
+ab = mk(M, H, H, 0, 1)
+timeit("attn_out_dgrad STORE", lambda i: ops.gemm(*ab[i], b_mn=True, epilogue=E.EPI_STORE, out=out_h), 2.0 * M * H * H)
+ab = mk(M, H, 3 * H, 0, 1)
+timeit("qkv_dgrad ADD", lambda i: ops.gemm(*ab[i], b_mn=True, res=res_h, epilogue=E.EPI_ADD, out=out_h), 2.0 * M * H * 3 * H)
+for nm, (m, n) in (("ffn2_wgrad", (H, I)), ("ffn1_wgrad", (I, H)), ("attn_out_wgrad", (H, H)), ("qkv_wgrad", (3 * H, H))):
+    ab = mk(m, n, M, 1, 1)
+    acc = torch.zeros(m, n, device=dev)
+    timeit(nm + " ATOMIC_F32", lambda i: ops.gemm(*ab[i], a_mn=True, b_mn=True, epilogue=E.EPI_ATOMIC_F32, out=acc), 2.0 * M * m * n)

@@ -5,7 +5,7 @@ import torch
 from meme_challenge_b200 import _lib, ops
 
 dev = "cuda"
-B, L, heads, H, I = 16, 164, 12, 768, 3072
+B, L, heads, H, I = int(os.environ.get("KB_B", "16")), 164, 12, 768, 3072
 M = B * L
 seed = torch.tensor([7], device=dev, dtype=torch.int64)
 
