@@ -197,6 +197,9 @@ int b200u_pos_linear_wgrad(const void* dp, const float* pos7, float* dW, int n, 
  * lse f32 [B,heads,L] is saved for the backward, which writes dqkv [B*L, 3H]. */
 int b200u_attention_fwd(const void* qkv, const float* mask, void* ctx, float* lse, int B, int L,
                         int num_heads, int H, const b200u_dropout_t* drop, b200u_stream_t stream);
+/* 1 (default) = tcgen05 / TMEM / TMA attention kernels (one CTA per sample x head x 128-query tile, thread =
+ * query row softmax); 0 = the warp-level mma.sync kernels (bring-up reference, differential tests). */
+int b200u_set_attention_impl(int tcgen05);
 /* scratch: caller-owned device buffer of b200u_attention_bwd_scratch_bytes(B, L, heads) bytes
  * (bf16 probabilities and score gradients handed from the dQ launch to the dK/dV launch; only
  * touched when L > 176, shorter sequences run the fused single-kernel backward).

@@ -22,6 +22,7 @@ SIGNATURES = {
     "b200u_set_sm_limit": (_i, [_i]),
     "b200u_set_bwd_streams": (_i, [_i]),
     "b200u_set_fused_layernorm": (_i, [_i]),
+    "b200u_set_attention_impl": (_i, [_i]),
     "b200u_prof_enable": (_i, [_i]),
     "b200u_prof_collect": (_i, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_i)]),
     "b200u_gemm": (_i, [_p, _p]),

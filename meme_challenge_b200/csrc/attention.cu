@@ -16,7 +16,22 @@
 #include "../../include/b200u.h"
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace b200u {
+
+// attention_tc.cu: tcgen05 / TMEM / TMA forward
+int attention_fwd_tc(const void* qkv, const float* mask, void* ctx, float* lse, int B, int L, int nh, int H,
+                     const b200u_dropout_t* drop, cudaStream_t stream);
+int attention_bwd_tc(const void* qkv, const float* mask, const void* ctx, const void* dctx, const float* lse,
+                     void* dqkv, float* dbias, int B, int L, int nh, int H, const b200u_dropout_t* drop,
+                     cudaStream_t stream);
+// b200u_set_attention_impl(): 1 (default) = tcgen05 kernels, 0 = the mma.sync kernels of this file
+// (B200U_ATTN_TC=0 selects them at load time)
+static int g_attn_tc = [] {
+    const char* e = getenv("B200U_ATTN_TC");
+    return (e && e[0] == '0') ? 0 : 1;
+}();
 
 constexpr int HD = 64;  // head dim (config/uniter-{base,large}.json: H / heads == 64)
 constexpr int TQ = 64;  // rows per CTA tile (4 warps x 16)
@@ -123,16 +138,6 @@ __device__ __forceinline__ void load_tiles_wait() {
     asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
-// Attention-probability dropout uses a one-round keyed hash (the score matrix is the largest
-// dropout site by far): key = f(seed, stream), sample pair = mix(pair_index ^ key).
-__device__ __forceinline__ uint32_t attn_key(uint64_t seed, uint32_t stream) {
-    return rng_mix((uint32_t)seed ^ (stream * 0x9E3779B9U)) ^ (uint32_t)(seed >> 32);
-}
-__device__ __forceinline__ uint32_t attn_rng(uint32_t key, uint32_t pair_idx) { return rng_mix(pair_idx ^ key); }
-__device__ __forceinline__ uint32_t attn_pair_base(int bh, int i, int L) {
-    return (uint32_t)((bh * L + i) * ((L + 1) >> 1));
-}
-
 constexpr float LOG2E = 1.4426950408889634f;
 
 // ---------------------------------------------------------------------------------------
@@ -177,7 +182,7 @@ attn_fwd_kernel(const bf16* __restrict__ qkv, const float* __restrict__ mask, bf
     const int g = lane >> 2, t2 = (lane & 3) * 2;
     const int i0 = r0 + g, i1 = r0 + g + 8;
     const uint32_t key = drop.thresh16 ? attn_key(load_seed(drop), drop.stream) : 0u;
-    const uint32_t pb0 = attn_pair_base(bh, i0, L), pb1 = attn_pair_base(bh, i1, L);
+    const uint32_t pb0 = attn_block_base(bh, i0, L), pb1 = attn_block_base(bh, i1, L);
     constexpr float SC = 0.125f * LOG2E;  // scores / sqrt(64) (model/layer.py:86), in log2 units
 
     // running max m and sum l of exp2(score2 - m), score2 = (q.k / 8 + mask) * log2(e)
@@ -232,7 +237,7 @@ attn_fwd_kernel(const bf16* __restrict__ qkv, const float* __restrict__ mask, bf
                     l1 += p[e][2] + p[e][3];
                     if (drop.thresh16) {  // dropout on the probabilities (model/layer.py:95)
                         const uint32_t jp = (uint32_t)(c0 + nt * 8 + t2) >> 1;
-                        const uint32_t h0 = attn_rng(key, pb0 + jp), h1 = attn_rng(key, pb1 + jp);
+                        const uint32_t h0 = attn_rng(key, pb0 + jp, i0 & 1), h1 = attn_rng(key, pb1 + jp, i1 & 1);
                         if ((h0 & 0xffffu) < drop.thresh16) p[e][0] = 0.f;
                         if ((h0 >> 16) < drop.thresh16) p[e][1] = 0.f;
                         if ((h1 & 0xffffu) < drop.thresh16) p[e][2] = 0.f;
@@ -338,7 +343,7 @@ attn_bwd_dq_kernel(const bf16* __restrict__ qkv, const float* __restrict__ mask,
     const int x0 = r0 + g, x1 = r0 + g + 8;
     uint32_t qa[4][4], da[4][4];
     float la = 0.f, lb = 0.f, Da = 0.f, Db = 0.f;
-    const uint32_t pb0 = attn_pair_base(bh, x0, L), pb1 = attn_pair_base(bh, x1, L);
+    const uint32_t pb0 = attn_block_base(bh, x0, L), pb1 = attn_block_base(bh, x1, L);
     constexpr float SC = 0.125f * LOG2E;
     bf16* pP0 = scrP + ((size_t)bh * L + x0) * LP;
     bf16* pP1 = scrP + ((size_t)bh * L + x1) * LP;
@@ -388,7 +393,7 @@ attn_bwd_dq_kernel(const bf16* __restrict__ qkv, const float* __restrict__ mask,
                     float k0 = 1.f, k1 = 1.f, k2 = 1.f, k3 = 1.f;
                     if (drop.thresh16) {
                         const uint32_t jp = (uint32_t)j >> 1;
-                        const uint32_t h0 = attn_rng(key, pb0 + jp), h1 = attn_rng(key, pb1 + jp);
+                        const uint32_t h0 = attn_rng(key, pb0 + jp, x0 & 1), h1 = attn_rng(key, pb1 + jp, x1 & 1);
                         k0 = ((h0 & 0xffffu) >= drop.thresh16) ? drop.scale : 0.f;
                         k1 = ((h0 >> 16) >= drop.thresh16) ? drop.scale : 0.f;
                         k2 = ((h1 & 0xffffu) >= drop.thresh16) ? drop.scale : 0.f;
@@ -593,7 +598,7 @@ attn_bwd_fused_kernel(const bf16* __restrict__ qkv, const float* __restrict__ ma
     const bool v0 = x0 < L, v1 = x1 < L;
     uint32_t qa[4][4], da[4][4];
     float la = 0.f, lb = 0.f, Da = 0.f, Db = 0.f;
-    const uint32_t pb0 = attn_pair_base(bh, x0, L), pb1 = attn_pair_base(bh, x1, L);
+    const uint32_t pb0 = attn_block_base(bh, x0, L), pb1 = attn_block_base(bh, x1, L);
     constexpr float SC = 0.125f * LOG2E;
     float dq[8][4];
 #pragma unroll
@@ -642,7 +647,7 @@ attn_bwd_fused_kernel(const bf16* __restrict__ qkv, const float* __restrict__ ma
                 float k0 = 1.f, k1 = 1.f, k2 = 1.f, k3 = 1.f;
                 if (drop.thresh16) {
                     const uint32_t jp = (uint32_t)j >> 1;
-                    const uint32_t h0 = attn_rng(key, pb0 + jp), h1 = attn_rng(key, pb1 + jp);
+                    const uint32_t h0 = attn_rng(key, pb0 + jp, x0 & 1), h1 = attn_rng(key, pb1 + jp, x1 & 1);
                     k0 = ((h0 & 0xffffu) >= drop.thresh16) ? drop.scale : 0.f;
                     k1 = ((h0 >> 16) >= drop.thresh16) ? drop.scale : 0.f;
                     k2 = ((h1 & 0xffffu) >= drop.thresh16) ? drop.scale : 0.f;
@@ -802,7 +807,16 @@ extern "C" int b200u_attention_fwd(const void* qkv, const float* mask, void* ctx
     if (B == 0) return B200U_OK;
     DropoutCfg dc = make_drop(drop);
     B200U_CHECK_ARG(dc.thresh16 == 0 || dc.seed_ptr, "attention_fwd: dropout needs seed_ptr");
+    if (g_attn_tc) {
+        B200U_CHECK_ARG(((uintptr_t)qkv & 15) == 0 && H % 8 == 0, "attention_fwd: qkv must be 16-byte aligned");
+        return attention_fwd_tc(qkv, mask, ctx, lse, B, L, num_heads, H, drop, stream);
+    }
     return launch_fwd(qkv, mask, ctx, lse, B, L, num_heads, H, dc, stream);
+}
+
+extern "C" int b200u_set_attention_impl(int tcgen05) {
+    g_attn_tc = tcgen05 ? 1 : 0;
+    return B200U_OK;
 }
 
 extern "C" size_t b200u_attention_bwd_scratch_bytes(int B, int L, int num_heads) {
@@ -821,5 +835,8 @@ extern "C" int b200u_attention_bwd(const void* qkv, const float* mask, const voi
     if (B == 0) return B200U_OK;
     DropoutCfg dc = make_drop(drop);
     B200U_CHECK_ARG(dc.thresh16 == 0 || dc.seed_ptr, "attention_bwd: dropout needs seed_ptr");
+    if (g_attn_tc && L <= 192 && ((uintptr_t)qkv & 15) == 0 && ((uintptr_t)dctx & 15) == 0 && ((uintptr_t)ctx & 15) == 0 &&
+        H % 8 == 0)
+        return attention_bwd_tc(qkv, mask, ctx, dctx, lse, dqkv, dbias_qkv, B, L, num_heads, H, drop, stream);
     return launch_bwd(qkv, mask, ctx, dctx, lse, dqkv, scratch, dbias_qkv, B, L, num_heads, H, dc, stream);
 }

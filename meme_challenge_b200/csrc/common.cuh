@@ -111,6 +111,34 @@ __device__ __forceinline__ uint64_t load_seed(const DropoutCfg& d) {
     return d.thresh16 ? *d.seed_ptr : 0ull;
 }
 
+// Dropout on the attention probabilities (model/layer.py:95). One hash serves a 2x2 block of the [L, L]
+// probability matrix of a (sample, head): idx = (bh * L2 + (i >> 1)) * L2 + (j >> 1), L2 = (L + 1) >> 1,
+//   x = (idx ^ key) * C1 ; x ^= x >> 15 ; (hi, lo) = x * C2  (one 32 x 32 -> 64 bit multiply)
+// query row i uses the word (i & 1) ? lo : hi, key column j its (j & 1) ? upper : lower 16 bits, and the
+// probability is kept when that sample >= thresh16. A thread that walks a row (forward: thread = query)
+// or a column (backward: thread = key) of the matrix therefore needs one hash per two scores either way,
+// and every kernel (tcgen05 and mma.sync, forward and backward) regenerates the same mask.
+__device__ __forceinline__ uint32_t attn_key(uint64_t seed, uint32_t stream) {
+    return rng_mix((uint32_t)seed ^ (stream * 0x9E3779B9U)) ^ (uint32_t)(seed >> 32);
+}
+__device__ __forceinline__ uint32_t attn_block_base(int bh, int i, int L) {
+    const int L2 = (L + 1) >> 1;
+    return (uint32_t)((bh * L2 + (i >> 1)) * L2);
+}
+__device__ __forceinline__ void attn_rng_block(uint32_t key, uint32_t block_idx, uint32_t& hi, uint32_t& lo) {
+    uint32_t x = (block_idx ^ key) * 0x9E3779B1u;
+    x ^= x >> 15;
+    const unsigned long long w = (unsigned long long)x * 0x85EBCA77ull;   // IMAD.WIDE
+    lo = (uint32_t)w;
+    hi = (uint32_t)(w >> 32);
+}
+// the word of query-row parity `i_odd` of block `block_idx` (= attn_block_base(bh, i, L) + (j >> 1))
+__device__ __forceinline__ uint32_t attn_rng(uint32_t key, uint32_t block_idx, int i_odd) {
+    uint32_t hi, lo;
+    attn_rng_block(key, block_idx, hi, lo);
+    return i_odd ? lo : hi;
+}
+
 // Programmatic dependent launch (see launch_k above). No-ops when launched without the attribute.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
@@ -488,6 +516,51 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
 }
 __device__ __forceinline__ void tmem_ld_wait() {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ---------------------------------------------------------------------------------------
+// UMMA descriptors (bit layout: cute/arch/mma_sm100_desc.hpp semantics restated).
+// ---------------------------------------------------------------------------------------
+// smem matrix descriptor, SWIZZLE_128B, version 1 (Blackwell).
+//  K-major : rows of 128 B (64 k-elements); 8-row groups SBO = 1024 B apart; LBO unused.
+//  MN-major: rows of 128 B (64 mn-elements), one row per k; 8-k groups SBO = 1024 B apart;
+//            next 64-wide mn block LBO bytes away (= one TMA box = BLOCK_K * 128 B).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes,
+                                                   uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;  // descriptor version
+    d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+    return d;
+}
+// descriptor without the start address (constant per operand layout)
+__host__ __device__ constexpr uint64_t desc_template(uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) |
+           ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// instruction descriptor for kind::f16, bf16 x bf16 -> f32.
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n, bool a_mn, bool b_mn) {
+    return (1u << 4)                      // D format f32
+           | (1u << 7)                    // A bf16
+           | (1u << 10)                   // B bf16
+           | ((a_mn ? 1u : 0u) << 15)     // A major
+           | ((b_mn ? 1u : 0u) << 16)     // B major
+           | ((uint32_t)(n >> 3) << 17)   // N
+           | ((uint32_t)(m >> 4) << 24);  // M
+}
+
+// 2-D bf16 / f32 tensor map of a row-major [rows, cols] matrix (leading dimension ld elements): boxes of
+// box_rows x 128 bytes, 128B-swizzled. Host side, defined in runtime.cu.
+int make_tmap(CUtensorMap* tm, const void* ptr, int rows, int cols, int ld, int box_rows, bool f32 = false);
+
+int make_tmap_3d(CUtensorMap* tm, const void* ptr, int batch, int rows, int cols, int ld, int box_rows);
+// 3-D tiled TMA store (smem box -> global, clipped per dimension), bulk-group completion.
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* tmap, const void* src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(tmap),
+                 "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
 }
 
 // Vector fp32 reduction into global memory (split-K wgrad accumulation).

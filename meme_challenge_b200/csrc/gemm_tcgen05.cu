@@ -178,36 +178,6 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;  // 64 bf16 = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
 
-// smem matrix descriptor, SWIZZLE_128B, version 1 (Blackwell).
-//  K-major : rows of 128 B (64 k-elements); 8-row groups SBO = 1024 B apart; LBO unused.
-//  MN-major: rows of 128 B (64 mn-elements), one row per k; 8-k groups SBO = 1024 B apart;
-//            next 64-wide mn block LBO bytes away (= one TMA box = BLOCK_K * 128 B).
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes,
-                                                   uint32_t sbo_bytes) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-    d |= (uint64_t)1 << 46;  // descriptor version
-    d |= (uint64_t)2 << 61;  // SWIZZLE_128B
-    return d;
-}
-// descriptor without the start address (constant per operand layout)
-__host__ __device__ constexpr uint64_t desc_template(uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    return ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) |
-           ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
-}
-// instruction descriptor for kind::f16, bf16 x bf16 -> f32.
-__host__ __device__ constexpr uint32_t make_idesc(int m, int n, bool a_mn, bool b_mn) {
-    return (1u << 4)                      // D format f32
-           | (1u << 7)                    // A bf16
-           | (1u << 10)                   // B bf16
-           | ((a_mn ? 1u : 0u) << 15)     // A major
-           | ((b_mn ? 1u : 0u) << 16)     // B major
-           | ((uint32_t)(n >> 3) << 17)   // N
-           | ((uint32_t)(m >> 4) << 24);  // M
-}
-
 constexpr int EPI_WARPS = 8;                      // warps 4..11
 constexpr int GEMM_THREADS = (4 + EPI_WARPS) * 32;  // 384
 
@@ -908,47 +878,9 @@ __global__ void gemm_simt_kernel(const bf16* __restrict__ A, int lda, int a_mn,
 // ---------------------------------------------------------------------------------------
 // Host side
 // ---------------------------------------------------------------------------------------
+extern long long* g_attn_dbg;  // attention_tc.cu
 static long long* g_dbg_ptr = nullptr;
 static int g_dbg_mode = 0;
-
-static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
-    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
-    if (!fn) {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) ==
-                cudaSuccess &&
-            qres == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
-    }
-    return fn;
-}
-
-// matrix stored as [rows, cols] row-major with leading dimension ld (elements); box = box_cols x
-// box_rows with a 128-byte swizzled inner dimension (64 bf16 or 32 f32 columns).
-static int make_tmap(CUtensorMap* tm, const void* ptr, int rows, int cols, int ld, int box_rows,
-                     bool f32 = false) {
-    auto fn = get_encode_fn();
-    if (!fn) {
-        set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
-        return B200U_ERR_CUDA;
-    }
-    const int esz = f32 ? 4 : 2;
-    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)ld * esz};
-    cuuint32_t box[2] = {(cuuint32_t)(128 / esz), (cuuint32_t)box_rows};
-    cuuint32_t estr[2] = {1u, 1u};
-    CUresult r = fn(tm, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
-                    const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-        set_error("cuTensorMapEncodeTiled failed (%d) ptr=%p rows=%d cols=%d ld=%d box_rows=%d f32=%d",
-                  (int)r, ptr, rows, cols, ld, box_rows, (int)f32);
-        return B200U_ERR_CUDA;
-    }
-    return B200U_OK;
-}
 
 template <int BLOCK_N, bool A_MN, bool B_MN, int EPI, int CLUSTER>
 static int launch_tc(const b200u_gemm_t* d, GemmArgs& g, cudaStream_t stream) {
@@ -1096,6 +1028,7 @@ extern "C" int b200u_gemm_debug_stamps(long long* device_ptr) {
     g_dbg_mode = (int)((uintptr_t)device_ptr & 3);
     device_ptr = (long long*)((uintptr_t)device_ptr & ~(uintptr_t)3);
     g_dbg_ptr = device_ptr;
+    g_attn_dbg = device_ptr;
     return B200U_OK;
 }
 

@@ -2,6 +2,7 @@
 #include "../../include/b200u.h"
 #include "common.cuh"
 
+#include <cudaTypedefs.h>
 #include <stdarg.h>
 #include <stdlib.h>
 
@@ -51,6 +52,68 @@ int num_sms() {
             return 148;
     }
     return (g_sm_limit > 0 && g_sm_limit < cached) ? g_sm_limit : cached;
+}
+
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) ==
+                cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+    }
+    return fn;
+}
+
+// matrix stored as [rows, cols] row-major with leading dimension ld (elements); box = box_cols x
+// box_rows with a 128-byte swizzled inner dimension (64 bf16 or 32 f32 columns).
+int make_tmap(CUtensorMap* tm, const void* ptr, int rows, int cols, int ld, int box_rows, bool f32) {
+    auto fn = get_encode_fn();
+    if (!fn) {
+        set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+        return B200U_ERR_CUDA;
+    }
+    const int esz = f32 ? 4 : 2;
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * esz};
+    cuuint32_t box[2] = {(cuuint32_t)(128 / esz), (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1u, 1u};
+    CUresult r = fn(tm, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                    const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d) ptr=%p rows=%d cols=%d ld=%d box_rows=%d f32=%d",
+                  (int)r, ptr, rows, cols, ld, box_rows, (int)f32);
+        return B200U_ERR_CUDA;
+    }
+    return B200U_OK;
+}
+
+// [batch, rows, cols] bf16 view of a row-major [batch * rows, cols] matrix (leading dimension ld): boxes of
+// 1 x box_rows x 64 columns, 128B-swizzled. Rows past `rows` are out of bounds PER SAMPLE: loads zero-fill
+// them, stores clip them, so a tile that overhangs a sample never touches its neighbour.
+int make_tmap_3d(CUtensorMap* tm, const void* ptr, int batch, int rows, int cols, int ld, int box_rows) {
+    auto fn = get_encode_fn();
+    if (!fn) {
+        set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+        return B200U_ERR_CUDA;
+    }
+    cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)batch};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)rows * ld * 2};
+    cuuint32_t box[3] = {64u, (cuuint32_t)box_rows, 1u};
+    cuuint32_t estr[3] = {1u, 1u, 1u};
+    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled(3d) failed (%d) ptr=%p batch=%d rows=%d cols=%d ld=%d box_rows=%d", (int)r,
+                  ptr, batch, rows, cols, ld, box_rows);
+        return B200U_ERR_CUDA;
+    }
+    return B200U_OK;
 }
 
 }  // namespace b200u
