@@ -116,9 +116,9 @@ def test_gemm_gelu_derivative_and_mul_colsum_epilogues():
     assert (cs.cpu() - out.float().sum(0).cpu()).abs().max() <= 1e-3 * out.float().sum(0).abs().max().cpu() + 1e-3
 
 
-@pytest.mark.parametrize("N", [128, 768, 1024])
-@pytest.mark.parametrize("M", [100, 2624])
-def test_gemm_fused_layernorm_epilogue(M, N):
+@pytest.mark.parametrize("N,block_n", [(128, 0), (768, 0), (1024, 0), (256, 256), (512, 256), (768, 256)])
+@pytest.mark.parametrize("M", [100, 2624, 5248])
+def test_gemm_fused_layernorm_epilogue(M, N, block_n):
     """EPI_BIAS_DROP_RES_LN: y = acc + bias + R (bf16) and LayerNorm(y) over the full row from ONE launch, the
     row statistics exchanged between the N/128 CTAs of a cluster (model/layer.py:111-115,152-156)."""
     _require_gpu()
@@ -133,14 +133,15 @@ def test_gemm_fused_layernorm_epilogue(M, N):
     beta = torch.randn(N, device=DEV) * 0.1
     mean = torch.empty(M, device=DEV)
     rstd = torch.empty(M, device=DEV)
-    y, x = ops.gemm(a, b, bias=bias, res=res, epilogue=_lib.EPI_BIAS_DROP_RES_LN,
+    y, x = ops.gemm(a, b, bias=bias, res=res, epilogue=_lib.EPI_BIAS_DROP_RES_LN, block_n=block_n,
                     ln=(gamma, beta, 1e-12, mean, rstd))
     y_ref = a.float().cpu() @ b.float().cpu().t() + bias.cpu() + res.float().cpu()
     assert (y.float().cpu() - y_ref).abs().max() <= 1e-2 * y_ref.abs().max()
     # LayerNorm of the bf16 values the kernel stored (what the standalone kernel and the backward see)
     yb = y.float().cpu()
     x_ref = torch.nn.functional.layer_norm(yb, (N,), gamma.cpu(), beta.cpu(), 1e-12)
-    assert (x.float().cpu() - x_ref).abs().max() <= 2e-2
+    # (bf16 output: one ulp is 2^-8 relative, and fp32 operation order may flip a rounding)
+    assert ((x.float().cpu() - x_ref).abs() <= 1e-2 + 8e-3 * x_ref.abs()).all()
     assert (mean.cpu() - yb.mean(1)).abs().max() <= 1e-4
     rs = 1.0 / torch.sqrt(yb.var(1, unbiased=False) + 1e-12)
     assert ((rstd.cpu() - rs).abs() / rs).max() <= 1e-4
@@ -148,12 +149,13 @@ def test_gemm_fused_layernorm_epilogue(M, N):
     y2 = ops.gemm(a, b, bias=bias, res=res, epilogue=_lib.EPI_BIAS_DROP_RES)
     assert torch.equal(y2, y)
     x2, mean2, rstd2 = ops.layernorm_fwd(y2, gamma, beta, 1e-12)
-    assert (x2.float() - x.float()).abs().max().item() <= 2e-2
+    assert ((x2.float() - x.float()).abs() <= 1e-2 + 8e-3 * x.float().abs()).all().item()
     assert (mean2 - mean).abs().max().item() <= 1e-5 and ((rstd2 - rstd).abs() / rstd2).max().item() <= 1e-5
     # dropout inside the fused epilogue draws the same mask as the unfused one (same counter stream)
     seed = torch.tensor([5], device=DEV, dtype=torch.int64)
     d = _lib.dropout_t(seed, 9, 0.1)
-    yd, _ = ops.gemm(a, b, bias=bias, res=res, epilogue=_lib.EPI_BIAS_DROP_RES_LN, drop=d, ln=(gamma, beta, 1e-12, None, None))
+    yd, _ = ops.gemm(a, b, bias=bias, res=res, epilogue=_lib.EPI_BIAS_DROP_RES_LN, drop=d, block_n=block_n,
+                     ln=(gamma, beta, 1e-12, None, None))
     yd2 = ops.gemm(a, b, bias=bias, res=res, epilogue=_lib.EPI_BIAS_DROP_RES, drop=d)
     assert torch.equal(yd, yd2)
 
@@ -664,10 +666,10 @@ def test_fused_window_equals_sequential_window():
     b0 = batches(0, True)[:1]
     logits = m(**_kw(b0[0]))
     loss = torch.nn.BCEWithLogitsLoss(pos_weight=torch.tensor([1.8], device=DEV))(logits.squeeze(1), b0[0]["labels"])
-    m.zero_grad()
+    ts.store.zero_grad()
     loss.backward()
-    want = torch.cat([p.grad.flatten() for p in m.parameters() if p.grad is not None]).norm().item() / 2.0
-    m.zero_grad()
+    want = ts.store.grad.norm().item() / 2.0     # every parameter gradient lives in the flat buffer
+    ts.store.zero_grad()
     ts.step(b0)
     assert abs(ts.gnorm.item() - want) <= 1e-3 * want
 

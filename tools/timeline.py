@@ -27,7 +27,7 @@ dev = torch.device("cuda", 0)
 torch.manual_seed(0)
 cfg = UniterConfig.from_dict(BASE)
 model = MemeUniter(UniterModel(cfg, 2048), BASE["hidden_size"], 1).to(dev).train()
-ts = TrainStep(model, gradient_accumulation=2)
+ts = TrainStep(model, gradient_accumulation=2, fuse_window="--fused" in sys.argv)
 bs = []
 for i in range(2):
     b = synth_batch(16, 64, 100, seed=1234 + i)
