@@ -201,7 +201,11 @@ struct GemmCfg {
     static constexpr int STG_PER_WARP = HAS_R ? 0 : 4096 * (DUAL ? 2 : 1);
     static constexpr int STG_BYTES = EPI_WARPS * STG_PER_WARP;
     static constexpr int R_GROUP_BYTES = BLOCK_M * 128;  // side input: one [128 x 64] bf16 box per group
-    static constexpr int R_BYTES = HAS_R ? NUM_GROUPS * R_GROUP_BYTES : 0;
+    // side-input slots: the LayerNorm epilogue keeps the whole row block (one slot per group); the others
+    // ping-pong over two slots (group g uses slot g & 1: the two warps of a quadrant walk even / odd groups),
+    // which leaves 256-wide tiles a 4-stage operand ring instead of 3
+    static constexpr int R_SLOTS = LN ? NUM_GROUPS : (NUM_GROUPS > 2 ? 2 : NUM_GROUPS);
+    static constexpr int R_BYTES = HAS_R ? R_SLOTS * R_GROUP_BYTES : 0;
     static constexpr int BIAS_BYTES = 2 * BLOCK_N * 4;  // one slot per accumulator stage
     // LayerNorm epilogue: gamma / beta slices of this CTA's columns + the row-statistics mailboxes the
     // cluster's CTAs push into: [2 buffers][8 source CTAs][2 column groups][128 rows] x (sum, M2)
@@ -412,19 +416,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (!Cfg::HAS_R) return;
             while (rt <= t_cur && rt < total_tiles) {
                 if (rn0 + rg * 64 < g.N) {
-                    const uint32_t par = ((rpar >> rg) & 1u) ^ 1u;
+                    const int rs = rg % Cfg::R_SLOTS;
+                    const uint32_t par = ((rpar >> rs) & 1u) ^ 1u;
                     if (block) {
-                        mbar_wait(&rempty[rg], par);
+                        mbar_wait(&rempty[rs], par);
                     } else {
-                        const int ok = __shfl_sync(0xffffffffu, (int)mbar_try_wait(&rempty[rg], par), 0);
+                        const int ok = __shfl_sync(0xffffffffu, (int)mbar_test_wait(&rempty[rs], par), 0);
                         if (!ok) return;
                     }
                     if (leader) {
-                        mbar_arrive_expect_tx_u(rfull_u + rg * 8, Cfg::R_GROUP_BYTES);
-                        tma_load_2d_u(sR_u + rg * Cfg::R_GROUP_BYTES, &tmR, rfull_u + rg * 8, rn0 + 64 * rg, rm0);
+                        mbar_arrive_expect_tx_u(rfull_u + rs * 8, Cfg::R_GROUP_BYTES);
+                        tma_load_2d_u(sR_u + rs * Cfg::R_GROUP_BYTES, &tmR, rfull_u + rs * 8, rn0 + 64 * rg, rm0);
                     }
                     __syncwarp();
-                    rpar ^= 1u << rg;
+                    rpar ^= 1u << rs;
                 }
                 if (++rg == NG) {
                     rg = 0;
@@ -443,7 +448,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int kb1 = min(g.num_kb, kb0 + g.kb_per_split);
             for (int kb = kb0; kb < kb1; ++kb) {
                 if (Cfg::HAS_R) {
-                    while (!mbar_try_wait(&empty[s], ph ^ 1)) r_pump(false);
+                    while (!mbar_test_wait(&empty[s], ph ^ 1)) r_pump(false);
                 } else {
                     mbar_wait(&empty[s], ph ^ 1);
                 }
@@ -669,7 +674,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const int col0 = gi * 64;
                     const int gn = gi + 2;
                     const bool more = gn < NG && n0 + gn * 64 < g.N;
-                    uint8_t* slot = Cfg::HAS_R ? sR + gi * Cfg::R_GROUP_BYTES : stg;
+                    const int rs = Cfg::HAS_R ? gi % Cfg::R_SLOTS : 0;   // side-input slot of this group
+                    uint8_t* slot = Cfg::HAS_R ? sR + rs * Cfg::R_GROUP_BYTES : stg;
                     uint8_t* dst = Cfg::HAS_R ? slot + q * (32 * 128) : stg;
                     tmem_ld_wait();                              // ra = columns col0 .. col0+31
                     tmem_ld_32x32(taddr + col0 + 32, rb);        // lands during the math on ra
@@ -677,8 +683,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     // (side-input epilogues write in place, a different slot per group: no wait here)
                     if (!Cfg::HAS_R && lane == 0) bulk_wait_read_all();
                     if (Cfg::HAS_R) {
-                        mbar_wait(&rfull[gi], (rpar >> gi) & 1u);
-                        rpar ^= 1u << gi;
+                        mbar_wait(&rfull[rs], (rpar >> rs) & 1u);
+                        rpar ^= 1u << rs;
                     }
                     __syncwarp();
 #pragma unroll
@@ -713,7 +719,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         tma_store_2d(&tmC, dst, n0 + col0, m0 + q * 32);
                         if (Cfg::DUAL) tma_store_2d(&tmC2, stg + 4096, n0 + col0, m0 + q * 32);
                         bulk_commit();
-                        if (Cfg::HAS_R && !Cfg::LN && prev >= 0) {
+                        if (Cfg::HAS_R && !Cfg::LN && Cfg::R_SLOTS == NG && prev >= 0) {
                             // all but the store just committed have been read: the previous group's
                             // side-input slot can be refilled for the next tile
                             bulk_wait_read_but_one();
@@ -736,6 +742,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         const int col = n0 + col0 + 2 * lane;
                         if (col < g.N) atomicAdd(g.colsum + col, c0);
                         if (col + 1 < g.N) atomicAdd(g.colsum + col + 1, c1);
+                    }
+                    if (Cfg::HAS_R && !Cfg::LN && Cfg::R_SLOTS < NG) {
+                        // ping-pong slots: this warp's next group reuses the slot, so it is handed back as soon
+                        // as the store has read it (and, EPI_MUL, every lane's column-sum reads are done)
+                        __syncwarp();
+                        if (lane == 0) {
+                            bulk_wait_read_all();
+                            mbar_arrive(&rempty[rs]);
+                        }
                     }
                     prev = gi;
                     gi = gn;
@@ -835,7 +850,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                     ++ln_tiles;
                     ln_s1 = 0.f;
-                } else if (Cfg::HAS_R && prev >= 0) {
+                } else if (Cfg::HAS_R && Cfg::R_SLOTS == NG && prev >= 0) {
                     __syncwarp();  // (EPI_MUL: every lane's column-sum reads of the slot are done)
                     if (lane == 0) {
                         bulk_wait_read_all();  // the last store has finished reading its side-input slot
