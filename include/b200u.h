@@ -305,14 +305,18 @@ int b200u_cosine_cost_bwd(const float* x, const float* y, const float* xinv, con
  * utils/optim_utils.py:16-46): grad averaging + clip_grad_norm_ + Adam with L2 weight decay,
  * refreshing the bf16 weight shadow. lr / step / coef live in device memory (graph replay). */
 int b200u_counter_add(unsigned long long* counter, unsigned long long inc, b200u_stream_t stream);
-int b200u_grad_sumsq(const float* g, size_t n, double* sumsq, b200u_stream_t stream);
+/* g16 / [lo16, hi16): optional bf16 gradient source for that element range (the data-parallel step
+ * all-reduces the encoder-layer buckets in bf16 and leaves them there); NULL = everything from g.
+ * run_wd[r] < 0 marks a run the optimizer skips (no gradient / frozen): only its gradient is zeroed. */
+int b200u_grad_sumsq(const float* g, size_t n, double* sumsq, const void* g16, size_t lo16, size_t hi16,
+                     b200u_stream_t stream);
 int b200u_clip_coef(const double* sumsq, float pre_scale, float max_norm, float* coef,
                     float* norm_out, b200u_stream_t stream);
 int b200u_adam_step(float* p, float* g, float* m, float* v, void* shadow_bf16, size_t n,
                     const long long* run_start, const float* run_wd, const int* chunk_run,
                     int num_runs, const float* coef, const float* lr,
                     const unsigned long long* step, float beta1, float beta2, float eps,
-                    int zero_grad, b200u_stream_t stream);
+                    int zero_grad, const void* g16, size_t lo16, size_t hi16, b200u_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -54,7 +54,7 @@ SIGNATURES = {
     "b200u_ot_distance": (_i, [_p, _p, _p, _i, _i, _i, _p]),
     "b200u_cosine_cost_bwd": (_i, [_p] * 10 + [_i, _i, _i, _i, _p]),
     "b200u_counter_add": (_i, [_p, _ull, _p]),
-    "b200u_grad_sumsq": (_i, [_p, _sz, _p, _p]),
+    "b200u_grad_sumsq": (_i, [_p, _sz, _p, _p, _sz, _sz, _p]),
     "b200u_clip_coef": (_i, [_p, _f, _f, _p, _p, _p]),
-    "b200u_adam_step": (_i, [_p, _p, _p, _p, _p, _sz, _p, _p, _p, _i, _p, _p, _p, _f, _f, _f, _i, _p]),
+    "b200u_adam_step": (_i, [_p, _p, _p, _p, _p, _sz, _p, _p, _p, _i, _p, _p, _p, _f, _f, _f, _i, _p, _sz, _sz, _p]),
 }

@@ -230,33 +230,58 @@ embedding_scatter_add_kernel(const bf16* __restrict__ d, const long long* __rest
 // into registers and does one plain read-modify-write of table_grad[id, :] -- no atomics, so identical
 // inputs give bit-identical tables on every rank (data-parallel sparse exchange of the word-embedding
 // gradient, train.py).
+// One warp per (run, 256-column chunk): lane l owns 8 consecutive columns. Frequent tokens ([CLS], [SEP] occur in
+// every sample) form runs of B * world rows, so the row loop keeps 8 row loads in flight (their source rows come
+// from one coalesced read of `perm`) and still adds them in sorted order: the sum order is fixed.
 __global__ void __launch_bounds__(256)
 embedding_segment_add_kernel(const bf16* __restrict__ d, const long long* __restrict__ ids_sorted,
                              const long long* __restrict__ perm, float* __restrict__ table_grad, int n,
-                             int H, long long padding_idx) {
+                             int H, long long padding_idx, int nchunk) {
     pdl_sync();
     const int lane = threadIdx.x & 31;
-    const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int p = w / nchunk, c = w - p * nchunk;
     if (p >= n) return;
     const long long id = ids_sorted[p];
     if (id == padding_idx) return;
     if (p > 0 && ids_sorted[p - 1] == id) return;  // not the first entry of its run
-    float* dst = table_grad + (size_t)id * H;
-    for (int v = lane; v < (H >> 3); v += 32) {
-        float acc[8];
+    const int col = c * 256 + lane * 8;
+    const bool active = col < H;
+    float acc[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) acc[k] = 0.f;
-        for (int q = p; q < n && ids_sorted[q] == id; ++q) {
-            uint4 u = *reinterpret_cast<const uint4*>(d + (size_t)perm[q] * H + v * 8);
-            const uint32_t* up = &u.x;
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    int q = p;
+    while (q < n) {
+        // lanes 0..7 probe the next 8 sorted entries; the warp learns how many still belong to this run
+        const int qq = q + (lane & 7);
+        const bool mine = qq < n && ids_sorted[qq] == id;
+        const long long src = mine ? perm[qq] : 0;
+        const unsigned m = __ballot_sync(0xffffffffu, mine) & 0xffu;
+        const int cnt = __ffs(~m & 0x1ffu) - 1;   // set bits are contiguous from bit 0 (sorted ids): run length, 0..8
+        if (cnt == 0) break;
+        uint4 u[8];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                float2 f = unpack_bf16(up[k]);
-                acc[2 * k] += f.x;
-                acc[2 * k + 1] += f.y;
+        for (int r = 0; r < 8; ++r) {
+            const long long sr = __shfl_sync(0xffffffffu, src, r);
+            u[r] = (r < cnt && active) ? *reinterpret_cast<const uint4*>(d + (size_t)sr * H + col) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            if (r < cnt) {
+                const uint32_t* up = &u[r].x;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float2 f = unpack_bf16(up[k]);
+                    acc[2 * k] += f.x;
+                    acc[2 * k + 1] += f.y;
+                }
             }
         }
-        float4* o = reinterpret_cast<float4*>(dst + v * 8);
+        if (cnt < 8) break;
+        q += 8;
+    }
+    if (active) {
+        float4* o = reinterpret_cast<float4*>(table_grad + (size_t)id * H + col);
         float4 a = o[0], b = o[1];
         a.x += acc[0]; a.y += acc[1]; a.z += acc[2]; a.w += acc[3];
         b.x += acc[4]; b.y += acc[5]; b.z += acc[6]; b.w += acc[7];
@@ -367,8 +392,10 @@ extern "C" int b200u_embedding_segment_add(const void* d, const long long* ids_s
     B200U_CHECK_ARG(d && ids_sorted && perm && table_grad, "embedding_segment_add: null pointer");
     B200U_CHECK_ARG(H % 8 == 0, "embedding_segment_add: H must be a multiple of 8");
     if (n == 0) return B200U_OK;
-    launch_k(embedding_segment_add_kernel, dim3((n + 7) / 8), dim3(256), 0, stream, (const bf16*)d, ids_sorted,
-             perm, table_grad, n, H, padding_idx);
+    const int nchunk = (H + 255) / 256;
+    const long long warps = (long long)n * nchunk;
+    launch_k(embedding_segment_add_kernel, dim3((unsigned)((warps + 7) / 8)), dim3(256), 0, stream, (const bf16*)d,
+             ids_sorted, perm, table_grad, n, H, padding_idx, nchunk);
     B200U_CHECK_LAUNCH("embedding_segment_add_kernel");
     return B200U_OK;
 }

@@ -72,6 +72,7 @@ class FlatStore(object):
         self.index = {}          # id(param) -> (offset, numel)
         self._shadow_version = None
         self._ptr_sig = None
+        self.touched = set()     # id(param) of every parameter a backward kernel has accumulated a gradient into
 
     # ------------------------------------------------------------------ build / validate
     def _signature(self):

@@ -17,7 +17,13 @@ P = _lib.ptr
 
 
 def grad_buf(p):
-    """fp32 accumulation target for parameter p (created zeroed if absent)."""
+    """fp32 accumulation target for parameter p (created zeroed if absent). Records that p receives a
+    gradient (the fused optimizer leaves parameters that never do untouched, like torch.optim.Adam skips
+    tensors whose .grad is None)."""
+    from .flat import store_of
+    st = store_of(p)
+    if st is not None:
+        st.touched.add(id(p))
     if p.grad is None:
         p.grad = torch.zeros_like(p, memory_format=torch.contiguous_format)
     return p.grad
@@ -121,6 +127,7 @@ def _layer_grads(layer, st):
     g.db2 = st.g32(layer.output.dense.bias).data_ptr()
     g.dln2_g = st.g32(layer.output.LayerNorm.weight).data_ptr()
     g.dln2_b = st.g32(layer.output.LayerNorm.bias).data_ptr()
+    st.touched.update(id(q) for q in layer.parameters())
     return g
 
 

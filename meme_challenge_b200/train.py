@@ -45,10 +45,18 @@ class GradBuckets(object):
     folded into the optimizer's gradient scale. Works on any backend (NCCL on GPUs, gloo in the
     CPU tests)."""
 
-    def __init__(self, entries, flat_grad, process_group=None, world=1):
+    def __init__(self, entries, flat_grad, process_group=None, world=1, comm_dtype=None):
         self.grad = flat_grad
         self.pg = process_group
         self.world = world
+        # comm_dtype=torch.bfloat16: the encoder-layer buckets (everything from layer 0 on) are cast to a
+        # bf16 staging buffer when their layer's backward is done and all-reduced THERE: half the NVLink
+        # volume; the fp32 accumulation over the window stays local and the optimizer reads the reduced
+        # bf16 values (b200u_adam_step g16 range). The embedding bucket stays fp32.
+        self.comm_dtype = comm_dtype
+        self.g16 = None
+        self.g16_lo = 0
+        self._cast_stream = None
         n = flat_grad.numel()
         first = {}
         for name, off in entries:
@@ -61,16 +69,41 @@ class GradBuckets(object):
         self.pending = []
         self.reduced = []
         self.sync = False  # True: blocking collectives on the current stream (graph-capturable)
+        if comm_dtype == torch.bfloat16 and world > 1 and len(self.segments) > 1:
+            self.g16_lo = self.segments[1][0]
+            self.g16 = torch.zeros(n - self.g16_lo, device=flat_grad.device, dtype=torch.bfloat16)
+
+    def bf16_range(self):
+        """(buffer, lo, hi) of the gradient range the optimizer must read as bf16, or (None, 0, 0)."""
+        if self.g16 is None:
+            return None, 0, 0
+        return self.g16, self.g16_lo, self.g16_lo + self.g16.numel()
 
     def reduce_bucket(self, idx):
         lo, hi = self.segments[idx]
         self.reduced.append(idx)
         if hi <= lo or self.world <= 1:
             return
+        buf = self.grad[lo:hi]
+        if self.g16 is not None and idx >= 1:
+            buf = self.g16[lo - self.g16_lo:hi - self.g16_lo]
+            if self.sync or not self.grad.is_cuda:
+                ops.cast_f32_to_bf16(self.grad[lo:hi], buf)
+            else:
+                # the fp32 -> bf16 cast of the bucket leaves the backward's critical stream: it runs on a side
+                # stream forked here, and the all-reduce (NCCL stream) is ordered behind it
+                cur = torch.cuda.current_stream()
+                if self._cast_stream is None:
+                    self._cast_stream = torch.cuda.Stream()
+                self._cast_stream.wait_stream(cur)
+                with torch.cuda.stream(self._cast_stream):
+                    ops.cast_f32_to_bf16(self.grad[lo:hi], buf)
+                    self.pending.append(torch.distributed.all_reduce(buf, group=self.pg, async_op=True))
+                return
         if self.sync:
-            torch.distributed.all_reduce(self.grad[lo:hi], group=self.pg)
+            torch.distributed.all_reduce(buf, group=self.pg)
         else:
-            self.pending.append(torch.distributed.all_reduce(self.grad[lo:hi], group=self.pg, async_op=True))
+            self.pending.append(torch.distributed.all_reduce(buf, group=self.pg, async_op=True))
 
     def wait(self):
         for w in self.pending:
@@ -83,7 +116,8 @@ class GradBuckets(object):
 class TrainStep(object):
     def __init__(self, model, lr=3e-5, weight_decay=1e-3, betas=(0.9, 0.999), eps=1e-8,
                  gradient_accumulation=2, max_grad_norm=5.0, pos_wt=1.8, process_group=None,
-                 overlap_comm=True, comm_sm_reserve=0, fuse_window=False):
+                 overlap_comm=True, comm_sm_reserve=0, fuse_window=False, comm_dtype=torch.bfloat16,
+                 frozen=(), data_parallel=True):
         self.model = model
         self.um = model.uniter_model
         self.accum = int(gradient_accumulation)
@@ -92,7 +126,9 @@ class TrainStep(object):
         self.betas, self.eps = betas, eps
         self.pg = process_group
         self.world = 1
-        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+        # data_parallel=False: a single-replica step even when a process group exists (reference runs in tests)
+        if data_parallel and (process_group is not None or
+                              (torch.distributed.is_available() and torch.distributed.is_initialized())):
             self.world = torch.distributed.get_world_size(process_group)
         self.overlap_comm = overlap_comm
         # SMs left to NCCL while bucket all-reduces overlap the last micro-batch's backward: the
@@ -105,6 +141,9 @@ class TrainStep(object):
         # accum * B samples (see _step_fused): same gradients, half the launches, twice the rows per GEMM
         self.fuse_window = bool(fuse_window)
         self._static_cat = None
+        self._ids_stream = None
+        self._ids_event = None
+        self._sumsq_done_from = None
 
         # one flat store for the whole MemeUniter (UNITER + classification head)
         store = FlatStore(model)
@@ -124,24 +163,18 @@ class TrainStep(object):
         self.base_lr = lr
         self.host_step = 0
 
-        # weight-decay runs over the flat layout
-        starts, wds = [], []
-        for name, p, off, cnt in store.entries:
-            wd = 0.0 if any(nd in name for nd in NO_DECAY) else float(weight_decay)
-            if not wds or wds[-1] != wd:
-                starts.append(off)
-                wds.append(wd)
-        starts[0] = 0
-        self.run_start = torch.tensor(starts + [n], device=dev, dtype=torch.int64)
-        self.run_wd = torch.tensor(wds, device=dev, dtype=torch.float32)
-        nchunks = (n + 1023) // 1024
-        chunk_first = torch.arange(nchunks, dtype=torch.int64) * 1024
-        cr = torch.searchsorted(torch.tensor(starts, dtype=torch.int64), chunk_first, right=True) - 1
-        self.chunk_run = cr.to(torch.int32).to(dev)
-        self.num_runs = len(wds)
+        # weight-decay runs over the flat layout. Parameters that get no gradient are SKIPPED, like
+        # torch.optim.Adam skips tensors whose .grad is None (the reference's fine-tuning never touches
+        # img_embeddings.mask_embedding.weight): `frozen` names / requires_grad=False up front, the rest is
+        # detected once from the first window's gradients (see optimizer_step).
+        self.weight_decay = float(weight_decay)
+        self.skip = set(n for n, p, _, _ in store.entries if (not p.requires_grad) or any(f in n for f in frozen))
+        self._skip_detected = False
+        self._build_runs()
 
         # gradient buckets: index 0 = embeddings, 1.. = encoder layers (the last also holds pooler + head)
-        self.comm = GradBuckets([(e[0], e[2]) for e in store.entries], store.grad, process_group, self.world)
+        self.comm = GradBuckets([(e[0], e[2]) for e in store.entries], store.grad, process_group, self.world,
+                                comm_dtype=comm_dtype)
         self.buckets = self.comm.segments
         self.comm.sync = not overlap_comm
         # Word-embedding gradient [vocab, H] (20 % of all parameters, produced LAST by every backward, so its
@@ -223,34 +256,60 @@ class TrainStep(object):
 
         return loss, probs
 
+    def _start_word_exchange(self, batches):
+        """Window start (data parallel): the token ids of the window are known BEFORE any compute, so their
+        exchange and the sort that orders the word-embedding rows for the deterministic segment add run on a
+        side stream beside the forward pass; after the last backward only the rows themselves travel."""
+        if not (self.world > 1 and self.overlap_comm and self.sparse_word and self.word_slice is not None):
+            return
+        dist = torch.distributed
+        cur = torch.cuda.current_stream()
+        if self._ids_stream is None:
+            self._ids_stream = torch.cuda.Stream()
+        s = self._ids_stream
+        s.wait_stream(cur)
+        with torch.cuda.stream(s):
+            ids = torch.cat([b["input_ids"].reshape(-1) for b in batches]).contiguous()
+            all_ids = torch.empty(self.world * ids.numel(), device=ids.device, dtype=ids.dtype)
+            dist.all_gather_into_tensor(all_ids, ids, group=self.pg)
+            self._ids_sorted, self._ids_perm = torch.sort(all_ids, stable=True)
+            self._ids_event = s.record_event()
+        for t in (self._ids_sorted, self._ids_perm):
+            t.record_stream(cur)
+
     def _finish_sparse_word(self):
         """Embedding bucket without the word table (dense, small) + the sparse word-row exchange."""
         dist = torch.distributed
         lo, hi, wp = self.word_slice
         b_lo, b_hi = self.buckets[0]
         self.comm.reduced.append(0)
-        for a, b in ((b_lo, min(lo, b_hi)), (max(hi, b_lo), b_hi)):
-            if b > a:
-                self.comm.pending.append(dist.all_reduce(self.store.grad[a:b], group=self.pg, async_op=True))
         pad = self._word_rows[0][2]
         cur = torch.cuda.current_stream()
         for r, i, _ in self._word_rows:      # earlier micro-batches produced their rows on the other stream
             r.record_stream(cur)
             i.record_stream(cur)
-        rows = torch.cat([r for r, _, _ in self._word_rows], 0)
-        ids = torch.cat([i for _, i, _ in self._word_rows], 0)
+        rows = self._word_rows[0][0] if len(self._word_rows) == 1 else torch.cat([r for r, _, _ in self._word_rows], 0)
         self._word_rows = None
         n, H = rows.shape
         all_rows = torch.empty(self.world * n, H, device=rows.device, dtype=rows.dtype)
-        all_ids = torch.empty(self.world * n, device=ids.device, dtype=ids.dtype)
-        dist.all_gather_into_tensor(all_rows, rows.contiguous(), group=self.pg)
-        dist.all_gather_into_tensor(all_ids, ids, group=self.pg)
-        # identical (all_rows, all_ids) on every rank + a deterministic, atomic-free segment add (rows sorted
-        # by id, each run summed in order) => bit-identical word-embedding gradients on all replicas
-        ids_sorted, perm = torch.sort(all_ids, stable=True)
+        layer_handles, self.comm.pending = self.comm.pending, []
+        gather = dist.all_gather_into_tensor(all_rows, rows.contiguous(), group=self.pg, async_op=True)
+        # the dense remainder of the embedding bucket (position / type tables, LayerNorms, image embedder)
+        # is reduced behind the row exchange, beside the segment add below
+        for a, b in ((b_lo, min(lo, b_hi)), (max(hi, b_lo), b_hi)):
+            if b > a:
+                self.comm.pending.append(dist.all_reduce(self.store.grad[a:b], group=self.pg, async_op=True))
+        # while those travel: squared norm of the (already reduced) encoder-layer range
+        self._sumsq_layers_early(layer_handles)
+        gather.wait()
+        # identical (all_rows, ids) on every rank + a deterministic, atomic-free segment add (rows sorted by
+        # id by the permutation computed at the window start, each run summed in order) => bit-identical
+        # word-embedding gradients on all replicas
+        cur.wait_event(self._ids_event)
         tot = self.world * n
-        ops._call("b200u_embedding_segment_add", P(all_rows), P(ids_sorted), P(perm), P(self.store.grad[lo:hi]),
-                  tot, H, C.c_longlong(pad))
+        assert self._ids_sorted.numel() == tot, "word-row exchange: ids of the window do not match its rows"
+        ops._call("b200u_embedding_segment_add", P(all_rows), P(self._ids_sorted), P(self._ids_perm),
+                  P(self.store.grad[lo:hi]), tot, H, C.c_longlong(pad))
 
     def micro_step(self, batch, last, first=True):
         return self._backward(self._forward_loss(batch, last, first))
@@ -317,18 +376,116 @@ class TrainStep(object):
         return outs
 
     # ------------------------------------------------------------------ optimizer
+    def _build_runs(self):
+        """Run table of b200u_adam_step over the flat layout: constant weight decay per run, -1 = skip."""
+        store, dev = self.store, self.dev
+        n = store.flat.numel()
+        starts, wds = [], []
+        for name, p, off, cnt in store.entries:
+            if name in self.skip:
+                wd = -1.0
+            else:
+                wd = 0.0 if any(nd in name for nd in NO_DECAY) else self.weight_decay
+            if not wds or wds[-1] != wd:
+                starts.append(off)
+                wds.append(wd)
+        starts[0] = 0
+        self.run_start = torch.tensor(starts + [n], device=dev, dtype=torch.int64)
+        self.run_wd = torch.tensor(wds, device=dev, dtype=torch.float32)
+        nchunks = (n + 1023) // 1024
+        chunk_first = torch.arange(nchunks, dtype=torch.int64) * 1024
+        cr = torch.searchsorted(torch.tensor(starts, dtype=torch.int64), chunk_first, right=True) - 1
+        self.chunk_run = cr.to(torch.int32).to(dev)
+        self.num_runs = len(wds)
+
+    def _detect_untouched(self):
+        """First optimizer step: parameters no backward kernel accumulated a gradient into during the first
+        window (unused branches such as img_embeddings.mask_embedding in fine-tuning) join the skip set,
+        matching torch.optim.Adam's `grad is None` behaviour. Host-side bookkeeping only (the Functions
+        record their gradient targets in FlatStore.touched), so it also works under CUDA-graph capture and
+        takes the same decision on every data-parallel rank."""
+        self._skip_detected = True
+        new = set(name for name, p, _, _ in self.store.entries if id(p) not in self.store.touched)
+        if not new.issubset(self.skip):
+            self.skip |= new
+            self._build_runs()
+
+    def _sumsq_layers_early(self, layer_handles):
+        """Data parallel, sparse word exchange: the squared norm of the encoder-layer range (75 % of the
+        gradient) is taken as soon as its buckets are reduced, beside the collectives of the embedding tail,
+        instead of after them; optimizer_step then only adds the embedding range."""
+        for h in layer_handles:
+            h.wait()
+        g16, lo16, hi16 = self.comm.bf16_range()
+        if g16 is None:
+            return
+        g = self.store.grad
+        self.sumsq.zero_()
+        # elements [lo16, hi16): read from the bf16 buffer; the call covers exactly that range
+        ops._call("b200u_grad_sumsq", P(g[lo16:hi16]), C.c_size_t(hi16 - lo16), P(self.sumsq), P(g16),
+                  C.c_size_t(0), C.c_size_t(hi16 - lo16))
+        self._sumsq_done_from = lo16
+
     def optimizer_step(self):
         self.comm.wait()
+        if not self._skip_detected:
+            self._detect_untouched()
         g = self.store.grad
         n = g.numel()
-        self.sumsq.zero_()
-        ops._call("b200u_grad_sumsq", P(g), C.c_size_t(n), P(self.sumsq))
+        g16, lo16, hi16 = self.comm.bf16_range()
+        if self._sumsq_done_from is not None:
+            # the layer range was summed early: add the embedding range [0, lo16) (fp32)
+            ops._call("b200u_grad_sumsq", P(g), C.c_size_t(self._sumsq_done_from), P(self.sumsq), None,
+                      C.c_size_t(0), C.c_size_t(0))
+            self._sumsq_done_from = None
+        else:
+            self.sumsq.zero_()
+            ops._call("b200u_grad_sumsq", P(g), C.c_size_t(n), P(self.sumsq), P(g16), C.c_size_t(lo16), C.c_size_t(hi16))
         pre = 1.0 / (self.accum * self.world)  # average_gradients + mean over ranks
         ops._call("b200u_clip_coef", P(self.sumsq), pre, self.max_grad_norm, P(self.coef), P(self.gnorm))
         ops.counter_add(self.step_t, 1)
         ops._call("b200u_adam_step", P(self.store.flat), P(g), P(self.m), P(self.v), P(self.store.shadow),
                   C.c_size_t(n), P(self.run_start), P(self.run_wd), P(self.chunk_run), self.num_runs,
-                  P(self.coef), P(self.lr_t), P(self.step_t), self.betas[0], self.betas[1], self.eps, 1)
+                  P(self.coef), P(self.lr_t), P(self.step_t), self.betas[0], self.betas[1], self.eps, 1,
+                  P(g16), C.c_size_t(lo16), C.c_size_t(hi16))
+
+    # ------------------------------------------------------------------ checkpoint / resume
+    def state_dict(self):
+        """Optimizer state in torch.optim.Adam's layout ('state': {index: step / exp_avg / exp_avg_sq} in
+        named_parameters() order, 'param_groups'), what the reference saves as `optimizer_state_dict`
+        (utils/save.py:57-64) so a run can be resumed by either implementation."""
+        step = int(self.step_t.item())
+        state = {}
+        for i, (name, p) in enumerate(self.model.named_parameters()):
+            off, cnt = self.store.index[id(p)]
+            state[i] = {"step": torch.tensor(float(step)), "exp_avg": self.m[off:off + cnt].view(p.shape).clone(),
+                        "exp_avg_sq": self.v[off:off + cnt].view(p.shape).clone()}
+        names = [n for n, _ in self.model.named_parameters()]
+        return {"state": state,
+                "param_groups": [{"lr": float(self.lr_t.item()), "betas": tuple(self.betas), "eps": self.eps,
+                                  "weight_decay": self.weight_decay, "params": list(range(len(names)))}],
+                "b200u": {"names": names, "host_step": self.host_step, "skip": sorted(self.skip)}}
+
+    def load_state_dict(self, sd):
+        params = list(self.model.named_parameters())
+        for i, (name, p) in enumerate(params):
+            st = sd["state"].get(i)
+            if st is None:
+                continue
+            off, cnt = self.store.index[id(p)]
+            self.m[off:off + cnt].copy_(st["exp_avg"].reshape(-1))
+            self.v[off:off + cnt].copy_(st["exp_avg_sq"].reshape(-1))
+        steps = [float(v["step"]) for v in sd["state"].values()]
+        self.step_t.fill_(int(max(steps)) if steps else 0)
+        if sd.get("param_groups"):
+            self.lr_t.fill_(float(sd["param_groups"][0]["lr"]))
+        extra = sd.get("b200u", {})
+        self.host_step = int(extra.get("host_step", self.host_step))
+        if "skip" in extra:
+            self.skip = set(extra["skip"])
+            self._skip_detected = True
+            self._build_runs()
+        self.store.refresh_shadow(force=True)
 
     def set_lr(self, lr):
         self.lr_t.fill_(lr)
@@ -348,6 +505,7 @@ class TrainStep(object):
         #  accumulation count, train_template.py:101-103: a shorter window is allowed, the scale is not changed)
         assert 1 <= len(batches) <= self.accum
         n = len(batches)
+        self._start_word_exchange(batches)
         if self.fuse_window and n > 1:
             outs = self._step_fused(batches, self._static_cat if batches is self._static else None)
         elif n == 1 or not self.pipeline:
@@ -417,8 +575,19 @@ class TrainStep(object):
                 self.step(static)
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
-        graph = torch.cuda.CUDAGraph()
         mode = "thread_local" if self.world > 1 else "global"
+        if not self._skip_detected:
+            # no eager step has run yet: a throw-away capture (nothing executes, no state changes) records
+            # which parameters receive gradients, so the optimizer's skip runs are final before the real one
+            self._skip_detected = True
+            hs = self.host_step
+            dry = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(dry, capture_error_mode=mode):
+                self.step(static)
+            del dry
+            self.host_step = hs
+            self._detect_untouched()
+        graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph, capture_error_mode=mode):
             outs = self.step(static)
         self._graph, self._static, self._static_out = graph, static, outs
@@ -430,6 +599,7 @@ class TrainStep(object):
                 v.copy_(src[k], non_blocking=True)
 
     def replay(self):
+        self.store.refresh_shadow()   # cheap when nothing changed; picks up load_state_dict / manual edits
         self._graph.replay()
         self.host_step += 1
         return self._static_out

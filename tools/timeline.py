@@ -23,14 +23,19 @@ BASE = dict(vocab_size=28996, hidden_size=768, num_hidden_layers=12, num_attenti
             initializer_range=0.02)
 if "--large" in sys.argv:
     BASE.update(hidden_size=1024, num_hidden_layers=24, num_attention_heads=16, intermediate_size=4096)
-dev = torch.device("cuda", 0)
+rank, world, lrank = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(lrank)
+dev = torch.device("cuda", lrank)
+if world > 1:
+    os.environ.setdefault("NCCL_MAX_CTAS", os.environ.get("TL_NCCL_CTAS", "16"))
+    torch.distributed.init_process_group("nccl", device_id=dev)
 torch.manual_seed(0)
 cfg = UniterConfig.from_dict(BASE)
 model = MemeUniter(UniterModel(cfg, 2048), BASE["hidden_size"], 1).to(dev).train()
 ts = TrainStep(model, gradient_accumulation=2, fuse_window="--fused" in sys.argv)
 bs = []
 for i in range(2):
-    b = synth_batch(16, 64, 100, seed=1234 + i)
+    b = synth_batch(16, 64, 100, seed=1234 + i + 100 * rank)
     b = {k: v.to(dev) for k, v in b.items() if torch.is_tensor(v)}
     b["labels"] = b["labels"].float()
     bs.append(b)
@@ -43,10 +48,19 @@ else:
 for _ in range(3):
     run()
 torch.cuda.synchronize()
-with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+if world > 1:
+    torch.distributed.barrier()
+if rank == 0:
+    with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+        for _ in range(2):
+            run()
+        torch.cuda.synchronize()
+else:
     for _ in range(2):
         run()
     torch.cuda.synchronize()
+    torch.distributed.barrier()
+    os._exit(0)
 os.makedirs("gpurun_out", exist_ok=True)
 path = "gpurun_out/%s_trace.json" % tag
 prof.export_chrome_trace(path)
@@ -61,3 +75,6 @@ with open("gpurun_out/%s_timeline.csv" % tag, "w") as f:
                                       e["name"].replace(",", ";")[:120]))
 os.remove(path)
 print("kernels:", len(ks), "span %.1f us" % (ks[-1]["ts"] + ks[-1]["dur"] - t0))
+if world > 1:
+    torch.distributed.barrier()
+    os._exit(0)
