@@ -82,7 +82,7 @@ class PinnedPrefetcher(object):
     item is requested). Non-tensor entries and `None`s pass through. labels are converted to float32 (the
     dtype the BCE kernel reads, train_template.py:99 `labels.float()`)."""
 
-    def __init__(self, source, device, depth=2):
+    def __init__(self, source, device, depth=2, auto_prefetch=True):
         if not torch.cuda.is_available():
             from .._lib import B200UError
             raise B200UError("PinnedPrefetcher needs a CUDA device (no CPU fallback)")
@@ -95,6 +95,10 @@ class PinnedPrefetcher(object):
         self.next_slot = 0
         self.h2d_bytes = 0       # bytes copied for the most recent item
         self._exhausted = False
+        # auto_prefetch=False: the consumer calls prefetch_next() itself, AFTER it has launched the step that
+        # consumes the current item, so the host time of issuing the next copies hides behind that step
+        self.auto_prefetch = bool(auto_prefetch)
+        self._pinned_ok = {}     # data_ptr -> bool (Tensor.is_pinned() queries the driver: cache per source buffer)
 
     # ------------------------------------------------------------------ internals
     def _buf(self, slot, name, t):
@@ -116,7 +120,11 @@ class PinnedPrefetcher(object):
             if k == "labels" and v.dtype != torch.float32:
                 v = v.float()
             pinned, dev = self._buf(slot, prefix + k, v)
-            if v.is_pinned():
+            key = (v.data_ptr(), v.numel())
+            is_pinned = self._pinned_ok.get(key)
+            if is_pinned is None:
+                is_pinned = self._pinned_ok[key] = bool(v.is_pinned())
+            if is_pinned:
                 src = v
             else:
                 pinned.copy_(v)
@@ -175,5 +183,12 @@ class PinnedPrefetcher(object):
         cur.wait_event(slot["ready"])
         slot["handed"] = True
         self.h2d_bytes = slot["bytes"]
-        self._issue()   # keep the pipeline full: the next item's copies start now
+        if self.auto_prefetch:
+            self._issue()   # keep the pipeline full: the next item's copies start now
         return slot["item"]
+
+    def prefetch_next(self):
+        """Issue the copies of the next item now (auto_prefetch=False: call it right after launching the work
+        that consumes the current item)."""
+        if len(self.queue) < self.depth - 1:
+            self._issue()

@@ -119,7 +119,7 @@ class TrainStep(object):
                  overlap_comm=True, comm_sm_reserve=0, fuse_window=False, comm_dtype=torch.bfloat16,
                  frozen=(), data_parallel=True):
         self.model = model
-        self.um = model.uniter_model
+        self.um = model.uniter_model if hasattr(model, "uniter_model") else model.uniter
         self.accum = int(gradient_accumulation)
         self.max_grad_norm = float(max_grad_norm)
         self.pos_wt = float(pos_wt)
@@ -603,3 +603,44 @@ class TrainStep(object):
         self._graph.replay()
         self.host_step += 1
         return self._static_out
+
+
+class PretrainStep(TrainStep):
+    """One optimizer step per task batch for `UniterForPretraining` (BASELINE config 5): MLM, MRFR and ITM with
+    the IPOT word-region alignment, round robin — the multi-task driver the reference only sketches
+    (`MetaLoader`, data/pretrain_meme_dataset.py:21-58, is never used by a trainer). The task losses are the
+    per-element losses `UniterForPretraining.forward(batch, task)` returns (model/pretrain.py:65-233), averaged;
+    the optimizer is the same fused Adam / clip step as fine-tuning with a window of one batch.
+
+    The word-embedding table is also the tied MLM decoder weight (model/layer.py:204-221), whose gradient is
+    dense, so the data-parallel step all-reduces the embedding bucket densely instead of exchanging rows."""
+
+    def __init__(self, model, tasks=("mlm", "mrfr", "itm"), **kw):
+        kw.setdefault("gradient_accumulation", 1)
+        super().__init__(model, **kw)
+        self.tasks = tuple(tasks)
+        self.sparse_word = False
+        self._task_i = 0
+
+    def task_step(self, batch, task=None):
+        """Forward + backward + optimizer step of one task batch. Returns (mean loss [1] device tensor, task)."""
+        if task is None:
+            task = self.tasks[self._task_i % len(self.tasks)]
+            self._task_i += 1
+        comm = self.world > 1
+        self.um._layer_grad_ready_cb = self._on_layer_done if (comm and self.overlap_comm) else None
+        self.um._sparse_word_cb = None
+        try:
+            loss_vec = self.model(batch, task, compute_loss=True)
+        finally:
+            self.um._layer_grad_ready_cb = None
+        loss = loss_vec.float().mean()
+        loss.backward()
+        if comm:
+            if not self.overlap_comm:
+                for i in range(len(self.buckets) - 1, 0, -1):
+                    self._allreduce_bucket(i)
+            self._allreduce_bucket(0)
+        self.optimizer_step()
+        self.host_step += 1
+        return loss.detach(), task

@@ -676,6 +676,101 @@ def test_fused_window_equals_sequential_window():
     assert abs(ts.gnorm.item() - want) <= 1e-3 * want
 
 
+def test_prefetcher_eval_path_and_optimizer_state_roundtrip(tmp_path):
+    """data.pipeline.PinnedPrefetcher feeds device batches that equal the host batches; evaluate.predict runs the
+    no-grad forward + sigmoid + BCE on them (probabilities equal the oracle's within the logit tolerance);
+    TrainStep.state_dict() round-trips through load_state_dict() (moments, step, skip set) and a resumed run
+    lands on the same parameters as an uninterrupted one."""
+    _require_gpu()
+    from meme_challenge_b200 import evaluate as E
+    from meme_challenge_b200.data.pipeline import PinnedPrefetcher
+    from meme_challenge_b200.train import TrainStep
+    cfg = dict(TINY)
+    cfg["hidden_dropout_prob"] = 0.0
+    cfg["attention_probs_dropout_prob"] = 0.0
+    host = []
+    for i in range(5):
+        b = O.synth_batch(4, 12, 10, seed=90 + i, variable=True, img_dim=IMG_DIM, vocab=TINY["vocab_size"], min_txt=2, min_bb=2)
+        hb = {k: v for k, v in b.items() if torch.is_tensor(v)}
+        hb["ids"] = torch.arange(4) + 10 * i
+        host.append(hb)
+    got = []
+    for db in PinnedPrefetcher(iter(host), DEV, depth=2):
+        got.append({k: v.clone() for k, v in db.items()})
+    assert len(got) == 5
+    for hb, db in zip(host, got):
+        for k in hb:
+            want = hb[k].float() if k == "labels" else hb[k]
+            assert torch.equal(db[k].cpu(), want), k
+    # evaluation path
+    m = _build(cfg, IMG_DIM, seed=4).eval()
+    probs, labels, loss, ids = E.predict(m, got, pos_wt=1.8)
+    ref_p = []
+    for hb in host:
+        ref_logits, _, _ = _oracle_run(m, cfg, hb, want_grads=False)
+        ref_p.append(torch.sigmoid(ref_logits.reshape(-1)))
+    ref_p = torch.cat(ref_p)
+    assert (probs.cpu() - ref_p).abs().max() <= 5e-3
+    assert torch.equal(ids.cpu(), torch.cat([hb["ids"] for hb in host]))
+    metrics = E.standard_metrics_binary(probs.cpu(), labels.cpu(), add_optimal_acc=True)
+    assert 0.0 <= metrics["aucroc"] <= 1.0 and metrics["optimal_accuracy"] >= metrics["accuracy"] - 1e-9
+    E.export_predictions(str(tmp_path / "preds.csv"), ids, probs, labels=labels)
+    assert len(open(str(tmp_path / "preds.csv")).read().splitlines()) == 21
+    # optimizer state: 2 steps + resume for 1 == 3 steps
+    def window(step):
+        return [got[(2 * step) % 5], got[(2 * step + 1) % 5]]
+    ma = _build(cfg, IMG_DIM, seed=5).train()
+    ta = TrainStep(ma, lr=1e-3, weight_decay=1e-3, gradient_accumulation=2)
+    for st in range(3):
+        ta.step(window(st))
+    mb = _build(cfg, IMG_DIM, seed=5).train()
+    tb = TrainStep(mb, lr=1e-3, weight_decay=1e-3, gradient_accumulation=2)
+    for st in range(2):
+        tb.step(window(st))
+    sd_model = {k: v.clone() for k, v in mb.state_dict().items()}
+    sd_opt = tb.state_dict()
+    assert set(sd_opt["state"][0]) == {"step", "exp_avg", "exp_avg_sq"} and float(sd_opt["state"][0]["step"]) == 2.0
+    mc = _build(cfg, IMG_DIM, sd_model, seed=99).train()
+    tc = TrainStep(mc, lr=1e-3, weight_decay=1e-3, gradient_accumulation=2)
+    tc.load_state_dict(sd_opt)
+    tc.step(window(2))
+    for (n, pa), (_, pc) in zip(ma.named_parameters(), mc.named_parameters()):
+        assert torch.allclose(pa, pc, rtol=1e-5, atol=1e-7), n
+    # parameters without a gradient (mask_embedding in fine-tuning) are left alone, like torch.optim.Adam
+    assert "uniter_model.img_embeddings.mask_embedding.weight" in ta.skip
+    w0 = _build(cfg, IMG_DIM, seed=5).uniter_model.img_embeddings.mask_embedding.weight
+    assert torch.equal(ma.uniter_model.img_embeddings.mask_embedding.weight.detach().cpu(), w0.detach().cpu())
+
+
+def test_pretrain_step_round_robin_decreases_losses():
+    """PretrainStep (BASELINE config 5 driver): MLM / MRFR / ITM(+IPOT) round robin with the fused optimizer;
+    a few steps on one repeated batch reduce every task's loss and keep all parameters finite."""
+    _require_gpu()
+    from meme_challenge_b200.data.synthetic import synth_pretrain_batch
+    from meme_challenge_b200.model.model import UniterConfig
+    from meme_challenge_b200.model.pretrain import UniterForPretraining
+    from meme_challenge_b200.train import PretrainStep
+    cfg = dict(TINY)
+    cfg["hidden_dropout_prob"] = 0.0
+    cfg["attention_probs_dropout_prob"] = 0.0
+    torch.manual_seed(0)
+    m = UniterForPretraining(UniterConfig.from_dict(cfg), IMG_DIM, 24).to(DEV).train()
+    b = synth_pretrain_batch(4, 12, 10, seed=77, img_dim=IMG_DIM, vocab=TINY["vocab_size"], label_dim=24, min_txt=2, min_bb=2)
+    d = {k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in b.items()}
+    d["ot_inputs"] = {k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in b["ot_inputs"].items()}
+    ts = PretrainStep(m, lr=2e-3, weight_decay=0.0, max_grad_norm=5.0)
+    first, last = {}, {}
+    for i in range(18):
+        loss, task = ts.task_step(d)
+        first.setdefault(task, float(loss.item()))
+        last[task] = float(loss.item())
+    assert set(first) == {"mlm", "mrfr", "itm"}
+    for t in first:
+        assert last[t] < first[t], (t, first[t], last[t])
+    assert all(torch.isfinite(p).all() for p in m.parameters())
+    assert m.last_ot_loss is not None   # the OT distances are computed (and dropped) like the reference does
+
+
 def test_data_parallel_replicas_identical_and_equal_single_process():
     """one process per GPU (torchrun, NCCL), gradient buckets all-reduced from the backward
     hooks, sparse word-embedding row exchange. tools/dp_check.py asserts that all ranks end with bit-identical

@@ -97,8 +97,9 @@ def test_no_cpu_fallback(built_lib):
 
 
 def test_bench_reference_arm_emits_one_contract_line():
-    """`bench.py --impl reference` (the reference's CPU path = the oracle port, no GPU needed) prints exactly
-    ONE JSON line on stdout carrying the contract keys; everything else goes to stderr."""
+    """`bench.py --impl reference` (the reference's own modules from oracle/_ref on the host cores, the oracle
+    port when they are absent; no GPU needed) prints exactly ONE JSON line on stdout carrying the contract keys;
+    everything else goes to stderr."""
     import json
     import os
     import subprocess
@@ -112,6 +113,92 @@ def test_bench_reference_arm_emits_one_contract_line():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["unit"] == "memes/s" and d["higher_is_better"] is True
     assert d["metric"] == "UNITER-base fwd+bwd memes/s" and d["value"] > 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"] == {"value": d["value"], "unit": "memes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and "model" not in d["config"]
+
+
+def test_synthetic_generators_match_the_oracle_generators():
+    """The package's synthetic batches (bench.py / smoke / tools) are what the golden fixtures were made with."""
+    from meme_challenge_b200.data.synthetic import synth_batch, synth_pretrain_batch
+    from oracle import uniter_oracle as O
+    for kw in (dict(B=4, T=12, R=10, seed=3, variable=True, img_dim=64, vocab=512, min_txt=2, min_bb=2),
+               dict(B=3, T=16, R=20, seed=9)):
+        a, b = O.synth_batch(**kw), synth_batch(**kw)
+        for k in a:
+            assert (torch.equal(a[k], b[k]) if torch.is_tensor(a[k]) else a[k] == b[k]), k
+    a = O.synth_pretrain_batch(4, 12, 10, seed=77, img_dim=64, vocab=512, label_dim=11, min_txt=2, min_bb=2)
+    b = synth_pretrain_batch(4, 12, 10, seed=77, img_dim=64, vocab=512, label_dim=11, min_txt=2, min_bb=2)
+    for k in a:
+        if torch.is_tensor(a[k]):
+            assert torch.equal(a[k], b[k]), k
+
+
+def test_metrics_against_reference_golden(golden_dir):
+    """evaluate.standard_metrics_binary (rank-statistic AUROC, one-sort threshold search) reproduces the
+    reference's data/metrics.py on the committed vectors, ties included."""
+    import numpy as np
+    from meme_challenge_b200 import evaluate as E
+    g = np.load(os.path.join(golden_dir, "metrics.npz"))
+    for i in range(int(g["n_cases"])):
+        p, l = torch.from_numpy(g["c%d_probs" % i]), torch.from_numpy(g["c%d_labels" % i])
+        m = E.standard_metrics_binary(p, l, add_optimal_acc=True)
+        for k in ("accuracy", "recall", "precision", "F1", "aucroc", "optimal_threshold", "optimal_accuracy"):
+            assert abs(m[k] - float(g["c%d_%s" % (i, k)])) <= 1e-6, (i, k, m[k], float(g["c%d_%s" % (i, k)]))
+    # sklearn agrees on AUROC for a random vector with ties
+    from sklearn.metrics import roc_auc_score
+    torch.manual_seed(5)
+    p = (torch.rand(500) * 20).round() / 20
+    l = (p + 0.4 * torch.randn(500) > 0.5).long()
+    assert abs(E.aucroc(p, l) - roc_auc_score(l.numpy(), p.numpy())) < 1e-12
+
+
+def test_export_predictions_csv_format(tmp_path):
+    from meme_challenge_b200 import evaluate as E
+    path = E.export_predictions(str(tmp_path / "p.csv"), torch.tensor([7, 42]), torch.tensor([0.25, 0.75]),
+                                labels=torch.tensor([0, 1]))
+    assert open(path).read() == "id,proba,label,gt\n7,0.250000,0,0\n42,0.750000,1,1\n"
+
+
+def test_collate_and_box_features_follow_the_reference():
+    """data/meme_dataset.py:152-214 + data/dataset_template.py:100-113: zero-padded features, arange position
+    ids, mask / gather index from the reference formulas (oracle restatement), 7-d boxes."""
+    from meme_challenge_b200.data.pipeline import box7, collate_memes
+    from oracle import uniter_oracle as O
+    torch.manual_seed(1)
+    bbox = torch.tensor([[10., 20., 110., 220.], [0., 0., 50., 40.]])
+    p = box7(bbox, 200., 400., normalize=True)
+    assert torch.allclose(p[0], torch.tensor([0.05, 0.05, 0.55, 0.55, 0.5, 0.5, 0.25]))
+    nbb = [3, 5, 2]
+    samples = [dict(img_feat=torch.randn(n, 8), img_pos_feat=torch.rand(n, 7), label=torch.tensor(i % 2),
+                    data_id=torch.tensor(100 + i)) for i, n in enumerate(nbb)]
+    input_ids = torch.randint(1, 50, (3, 6))
+    tl = [4, 6, 2]
+    for valid in (True, False):
+        b = collate_memes(samples, input_ids, tl, pad_regions_are_valid=valid)
+        assert b["img_feat"].shape == (3, 5, 8) and torch.equal(b["img_feat"][0, 3:], torch.zeros(2, 8))
+        assert torch.equal(b["position_ids"], torch.arange(6).unsqueeze(0).repeat(3, 1))
+        il = [5] * 3 if valid else nbb     # the reference reads the region count off the padded tensor
+        am = O.get_attention_mask(tl, il)
+        assert torch.equal(b["attn_mask"], am)
+        assert torch.equal(b["gather_index"], O.get_gather_index(tl, il, 3, 6, am.shape[1]))
+        assert torch.equal(b["ids"], torch.tensor([100, 101, 102]))
+
+
+def test_reference_loader_runs_the_unmodified_reference():
+    """oracle/ref_loader.py imports the reference modules (oracle/_ref when built, else the checkout) with the
+    two shims; the reference MemeUniter runs a forward on the package's synthetic batch."""
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("no reference checkout and oracle/_ref not built")
+    ns = ref_loader.load()
+    from meme_challenge_b200.data.synthetic import synth_batch
+    cfg = ns.model.UniterConfig.from_dict(TINY)
+    torch.manual_seed(0)
+    m = ns.meme_uniter.MemeUniter(ns.model.UniterModel(cfg, IMG_DIM), cfg.hidden_size, 1).eval()
+    b = synth_batch(2, 6, 4, img_dim=IMG_DIM, vocab=TINY["vocab_size"], min_txt=2, min_bb=2)
+    with torch.no_grad():
+        out = m(input_ids=b["input_ids"], position_ids=b["position_ids"], img_feat=b["img_feat"],
+                img_pos_feat=b["img_pos_feat"], attention_mask=b["attn_mask"], gather_index=b["gather_index"],
+                output_all_encoded_layers=False)
+    assert out.shape == (2, 1) and torch.isfinite(out).all()
