@@ -56,10 +56,11 @@ __device__ __forceinline__ void stats(const float (&x)[EMB_MAXV][8], int nv, int
 __device__ __forceinline__ void apply_dropout8(float (&o)[8], uint64_t seed, const DropoutCfg& drop,
                                                size_t elem0) {
     if (!drop.thresh16) return;
-    const uint32_t pbase = (uint32_t)(elem0 >> 1);
+    uint32_t hw[4];
+    rng_words8(seed, drop.stream, elem0, hw);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        uint32_t h = rng_pair(seed, drop.stream, pbase + j);
+        uint32_t h = hw[j];
         o[2 * j] = ((h & 0xffffu) >= drop.thresh16) ? o[2 * j] * drop.scale : 0.f;
         o[2 * j + 1] = ((h >> 16) >= drop.thresh16) ? o[2 * j + 1] * drop.scale : 0.f;
     }

@@ -275,10 +275,14 @@ __device__ __forceinline__ void epi_math8(const uint32_t* acc, const float* bias
         for (int i = 0; i < 4; ++i) out[i] = f2_to_bf16x2(f2_add(v[i], f2_from_bf16x2(rr[i])));
     } else if (EPI == B200U_EPI_BIAS_DROP_RES || EPI == B200U_EPI_BIAS_DROP_RES_LN) {
         if (g.drop.thresh16) {
-            const uint32_t pbase = (uint32_t)(((size_t)row * g.N + col) >> 1);
+            // 8 consecutive columns starting at a multiple of 8 = two hash quads (pairs 2q, 2q+1 share a hash)
+            const uint32_t qbase = (uint32_t)(((size_t)row * g.N + col) >> 2);
+            uint32_t hw[4];
+            rng_quad(seed, g.drop.stream, qbase, hw[0], hw[1]);
+            rng_quad(seed, g.drop.stream, qbase + 1, hw[2], hw[3]);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const uint32_t h = rng_pair(seed, g.drop.stream, pbase + i);
+                const uint32_t h = hw[i];
                 const float m0 = ((h & 0xffffu) >= g.drop.thresh16) ? g.drop.scale : 0.f;
                 const float m1 = ((h >> 16) >= g.drop.thresh16) ? g.drop.scale : 0.f;
                 out[i] = f2_to_bf16x2(f2_fma(v[i], f2(m0, m1), f2_from_bf16x2(rr[i])));

@@ -102,10 +102,11 @@ layernorm_fwd_kernel(const TIn* __restrict__ x, const float* __restrict__ gamma,
 #pragma unroll
             for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rstd * g[j] + b[j];
             if (drop.thresh16) {
-                const uint32_t pbase = (uint32_t)(((size_t)row * H + vi * 8) >> 1);
+                uint32_t hw[4];
+                rng_words8(seed, drop.stream, (size_t)row * H + vi * 8, hw);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    uint32_t h = rng_pair(seed, drop.stream, pbase + j);
+                    uint32_t h = hw[j];
                     o[2 * j] = ((h & 0xffffu) >= drop.thresh16) ? o[2 * j] * drop.scale : 0.f;
                     o[2 * j + 1] = ((h >> 16) >= drop.thresh16) ? o[2 * j + 1] * drop.scale : 0.f;
                 }
@@ -178,10 +179,11 @@ layernorm_bwd_kernel(const bf16* __restrict__ dy, const TX* __restrict__ x,
                     load8(gamma + vi * 8, g);
                     if (drop_on_input && drop.thresh16) {
                         // y = dropout(LN(x)) (embedding modules): the incoming grad is masked first
-                        const uint32_t pbase = (uint32_t)(((size_t)row * H + vi * 8) >> 1);
+                        uint32_t hw[4];
+                rng_words8(seed, drop.stream, (size_t)row * H + vi * 8, hw);
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            uint32_t h = rng_pair(seed, drop.stream, pbase + j);
+                            uint32_t h = hw[j];
                             gd[i][2 * j] = ((h & 0xffffu) >= drop.thresh16) ? gd[i][2 * j] * drop.scale : 0.f;
                             gd[i][2 * j + 1] = ((h >> 16) >= drop.thresh16) ? gd[i][2 * j + 1] * drop.scale : 0.f;
                         }
@@ -213,10 +215,11 @@ layernorm_bwd_kernel(const bf16* __restrict__ dy, const TX* __restrict__ x,
                     if (dx) store8(dx + (size_t)row * H + vi * 8, o);
                     if (dz) {
                         if (drop.thresh16 && !drop_on_input) {
-                            const uint32_t pbase = (uint32_t)(((size_t)row * H + vi * 8) >> 1);
+                            uint32_t hw[4];
+                rng_words8(seed, drop.stream, (size_t)row * H + vi * 8, hw);
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
-                                uint32_t h = rng_pair(seed, drop.stream, pbase + j);
+                                uint32_t h = hw[j];
                                 o[2 * j] = ((h & 0xffffu) >= drop.thresh16) ? o[2 * j] * drop.scale : 0.f;
                                 o[2 * j + 1] = ((h >> 16) >= drop.thresh16) ? o[2 * j + 1] * drop.scale : 0.f;
                             }
