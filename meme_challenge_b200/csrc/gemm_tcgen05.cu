@@ -789,13 +789,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     // with st.async: each store completes 8 transaction bytes on the destination's barrier, which
                     // one local thread armed with the byte count of the whole exchange
                     const int buf = ln_tiles & 1;
-                    if (ew == 0 && lane == 0) mbar_arrive_expect_tx(&lnbar[buf], (uint32_t)(g.ln_cl * 2 * BLOCK_M * 8));
-                    const uint32_t mbox = smem_u32(sPart + ((buf * Cfg::LN_MAX_CL + ln_rank) * 2 + half) * BLOCK_M + rr);
-                    const uint32_t lb = smem_u32(&lnbar[buf]);
-                    for (int r = 0; r < g.ln_cl; ++r)
-                        dsmem_st_async_f32x2(dsmem_addr(mbox, (uint32_t)r), ln_s1, m2, dsmem_addr(lb, (uint32_t)r));
-                    // (3) all 2 * cluster-size partials of the row have landed here: Chan's combination
-                    mbar_wait_cluster(&lnbar[buf], (uint32_t)(ln_tiles >> 1) & 1u);
+                    if (g.ln_cl == 1) {
+                        // one column tile covers the row: only this CTA's two halves meet, through plain shared
+                        // memory and the epilogue warps' named barrier (no distributed shared memory involved)
+                        sPart[((buf * Cfg::LN_MAX_CL) * 2 + half) * BLOCK_M + rr] = make_float2(ln_s1, m2);
+                        asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+                    } else {
+                        if (ew == 0 && lane == 0) mbar_arrive_expect_tx(&lnbar[buf], (uint32_t)(g.ln_cl * 2 * BLOCK_M * 8));
+                        const uint32_t mbox = smem_u32(sPart + ((buf * Cfg::LN_MAX_CL + ln_rank) * 2 + half) * BLOCK_M + rr);
+                        const uint32_t lb = smem_u32(&lnbar[buf]);
+                        for (int r = 0; r < g.ln_cl; ++r)
+                            dsmem_st_async_f32x2(dsmem_addr(mbox, (uint32_t)r), ln_s1, m2, dsmem_addr(lb, (uint32_t)r));
+                        // (3) all 2 * cluster-size partials of the row have landed here: Chan's combination
+                        mbar_wait_cluster(&lnbar[buf], (uint32_t)(ln_tiles >> 1) & 1u);
+                    }
                     float tot = 0.f;
                     const float2* pp = sPart + (size_t)buf * Cfg::LN_MAX_CL * 2 * BLOCK_M + rr;
                     for (int r = 0; r < 2 * g.ln_cl; ++r) tot += pp[r * BLOCK_M].x;
