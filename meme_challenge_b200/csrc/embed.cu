@@ -11,6 +11,8 @@
 #include "../../include/b200u.h"
 #include "common.cuh"
 
+#include <mutex>
+
 namespace b200u {
 
 constexpr int EMB_MAXV = 4;  // H <= 1024
@@ -130,28 +132,60 @@ img_embed_fwd_kernel(const float* __restrict__ a, const float* __restrict__ pos7
                      bf16* __restrict__ out, float* __restrict__ p_out, float* __restrict__ s_out,
                      float* __restrict__ stats_out, int n, int H, float eps, DropoutCfg drop) {
     pdl_sync();
+    // Everything that does not depend on the row is staged once per CTA with 16-byte loads in ONE round trip:
+    // pos_linear's weight [H][7] (a lane's 8 consecutive features are 56 contiguous floats) and bias, the three
+    // LayerNorms' gamma / beta and token-type rows 0 and 1. The row's own loads are issued before the staging so
+    // both latencies overlap; after the barrier the kernel only touches shared memory until its stores.
+    extern __shared__ __align__(16) float sWp[];   // [H * 7] weight | [H] bias | 6 x [H] LN vectors | 2 x [H] type rows
+    float* sVec = sWp + (size_t)H * 8;
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (row >= n) return;
+    const bool valid = row < n;
     const int nv = H >> 3;
     float pf[7];
-#pragma unroll
-    for (int c = 0; c < 7; ++c) pf[c] = pos7[(size_t)row * 7 + c];
-    const long long tid = type_ids ? type_ids[row] : 1;  // model.py:313-314 default ones
-
+    long long tid = 1;  // model.py:313-314 default ones
     float xa[EMB_MAXV][8], xp[EMB_MAXV][8];
+    if (valid) {
+#pragma unroll
+        for (int c = 0; c < 7; ++c) pf[c] = pos7[(size_t)row * 7 + c];
+        if (type_ids) tid = type_ids[row];
+#pragma unroll
+        for (int i = 0; i < EMB_MAXV; ++i)
+            if (lane + 32 * i < nv) ld8f(a + (size_t)row * H + (lane + 32 * i) * 8, xa[i]);
+    }
+    {
+        const int nvec = (H * 7) >> 2, hv = H >> 2;   // H % 8 == 0
+        for (int i = threadIdx.x; i < nvec; i += blockDim.x)
+            reinterpret_cast<float4*>(sWp)[i] = reinterpret_cast<const float4*>(Wpos)[i];
+        const float* vecs[8] = {g_img, b_img, g_pos, b_pos, g, be, type, type + H};
+        for (int i = threadIdx.x; i < hv; i += blockDim.x) {
+            reinterpret_cast<float4*>(sWp + H * 7)[i] = reinterpret_cast<const float4*>(bpos)[i];
+#pragma unroll
+            for (int v = 0; v < 8; ++v)
+                reinterpret_cast<float4*>(sVec + (size_t)v * H)[i] = reinterpret_cast<const float4*>(vecs[v])[i];
+        }
+    }
+    __syncthreads();
+    if (!valid) return;
+    const float* ty_row = (tid >= 0 && tid < 2) ? sVec + (size_t)(6 + tid) * H : type + (size_t)tid * H;
+
 #pragma unroll
     for (int i = 0; i < EMB_MAXV; ++i) {
         const int vi = lane + 32 * i;
         if (vi < nv) {
-            ld8f(a + (size_t)row * H + vi * 8, xa[i]);
+            float wflat[56], bv[8];
+#pragma unroll
+            for (int q = 0; q < 14; ++q) {
+                const float4 t4 = *reinterpret_cast<const float4*>(sWp + (size_t)vi * 56 + 4 * q);
+                wflat[4 * q] = t4.x; wflat[4 * q + 1] = t4.y; wflat[4 * q + 2] = t4.z; wflat[4 * q + 3] = t4.w;
+            }
+            ld8f(sWp + H * 7 + vi * 8, bv);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const float* w = Wpos + (size_t)(vi * 8 + j) * 7;
                 float acc = 0.f;
 #pragma unroll
-                for (int c = 0; c < 7; ++c) acc = fmaf(pf[c], w[c], acc);
-                xp[i][j] = acc + bpos[vi * 8 + j];
+                for (int c = 0; c < 7; ++c) acc = fmaf(pf[c], wflat[j * 7 + c], acc);
+                xp[i][j] = acc + bv[j];
             }
             if (p_out) st8f(p_out + (size_t)row * H + vi * 8, xp[i]);
         }
@@ -164,9 +198,9 @@ img_embed_fwd_kernel(const float* __restrict__ a, const float* __restrict__ pos7
         const int vi = lane + 32 * i;
         if (vi < nv) {
             float gi[8], bi[8], gp[8], bp[8], ty[8];
-            ld8f(g_img + vi * 8, gi); ld8f(b_img + vi * 8, bi);
-            ld8f(g_pos + vi * 8, gp); ld8f(b_pos + vi * 8, bp);
-            ld8f(type + (size_t)tid * H + vi * 8, ty);
+            ld8f(sVec + vi * 8, gi); ld8f(sVec + H + vi * 8, bi);
+            ld8f(sVec + 2 * H + vi * 8, gp); ld8f(sVec + 3 * H + vi * 8, bp);
+            ld8f(ty_row + vi * 8, ty);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const float t1 = (xa[i][j] - m1) * r1 * gi[j] + bi[j];
@@ -188,8 +222,8 @@ img_embed_fwd_kernel(const float* __restrict__ a, const float* __restrict__ pos7
         const int vi = lane + 32 * i;
         if (vi < nv) {
             float gg[8], bb[8], o[8];
-            ld8f(g + vi * 8, gg);
-            ld8f(be + vi * 8, bb);
+            ld8f(sVec + 4 * H + vi * 8, gg);
+            ld8f(sVec + 5 * H + vi * 8, bb);
 #pragma unroll
             for (int j = 0; j < 8; ++j) o[j] = (xa[i][j] - m3) * r3 * gg[j] + bb[j];
             apply_dropout8(o, seed, drop, (size_t)row * H + vi * 8);
@@ -199,30 +233,64 @@ img_embed_fwd_kernel(const float* __restrict__ a, const float* __restrict__ pos7
 }
 
 // table_grad[ids[r], :] += d[r, :]   (nn.Embedding backward; rows with ids == padding_idx skipped)
-__global__ void __launch_bounds__(256)
+// One warp per (position t, 256-column chunk, segment of 8 samples): it loads the segment's rows b*T + t together
+// and keeps the running sum of consecutive rows with the SAME id in registers, flushing (two 16-byte vector
+// reductions per lane) only when the id changes. Position ids repeat down the batch (one flush per segment instead
+// of 8 colliding atomics per element) and so do [CLS] / [SEP]; distinct ids cost one flush each.
+__global__ void __launch_bounds__(64)
 embedding_scatter_add_kernel(const bf16* __restrict__ d, const long long* __restrict__ ids,
                              int ids_batch_stride, int T, long long const_id, float* __restrict__ table_grad,
-                             int n, int H, long long padding_idx) {
+                             int n, int H, long long padding_idx, int nchunk, int nseg) {
     pdl_sync();
     const int lane = threadIdx.x & 31;
-    const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (r >= n) return;
-    long long id = const_id;
-    if (ids) {
-        const int b = r / T, t = r - b * T;
-        id = ids[(size_t)b * ids_batch_stride + t];
-    }
-    if (id == padding_idx) return;
-    float* dst = table_grad + (size_t)id * H;
-    for (int v = lane; v < (H >> 3); v += 32) {
-        uint4 u = *reinterpret_cast<const uint4*>(d + (size_t)r * H + v * 8);
-        const uint32_t* up = &u.x;
+    int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int c = w % nchunk;
+    w /= nchunk;
+    const int seg = w % nseg, t = w / nseg;
+    if (t >= T) return;
+    const int B = n / T;
+    const int b0 = seg * 8;
+    const int col = c * 256 + lane * 8;
+    if (col >= H) return;
+    const int bb = b0 + (lane & 7);
+    long long my_id = const_id;
+    if (ids && bb < B) my_id = ids[(size_t)bb * ids_batch_stride + t];
+    uint4 u[8];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            float2 f = unpack_bf16(up[k]);
-            atomicAdd(dst + v * 8 + 2 * k, f.x);
-            atomicAdd(dst + v * 8 + 2 * k + 1, f.y);
+    for (int r = 0; r < 8; ++r)
+        u[r] = (b0 + r < B) ? *reinterpret_cast<const uint4*>(d + ((size_t)(b0 + r) * T + t) * H + col)
+                            : make_uint4(0, 0, 0, 0);
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    long long cur = padding_idx;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const long long id = __shfl_sync(0xffffffffu, my_id, r);
+        if (b0 + r < B) {
+            if (id != cur) {
+                if (cur != padding_idx) {
+                    float* dst = table_grad + (size_t)cur * H + col;
+                    red_add_v4(dst, acc[0], acc[1], acc[2], acc[3]);
+                    red_add_v4(dst + 4, acc[4], acc[5], acc[6], acc[7]);
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+                cur = id;
+            }
+            const uint32_t* up = &u[r].x;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float2 f = unpack_bf16(up[k]);
+                acc[2 * k] += f.x;
+                acc[2 * k + 1] += f.y;
+            }
         }
+    }
+    if (cur != padding_idx) {
+        float* dst = table_grad + (size_t)cur * H + col;
+        red_add_v4(dst, acc[0], acc[1], acc[2], acc[3]);
+        red_add_v4(dst + 4, acc[4], acc[5], acc[6], acc[7]);
     }
 }
 
@@ -290,37 +358,52 @@ embedding_segment_add_kernel(const bf16* __restrict__ d, const long long* __rest
     }
 }
 
-// dW[h, c] += sum_r dp[r, h] * pos7[r, c]   (pos_linear weight grad, K = 7). One thread per h.
+// dW[h, c] += sum_r dp[r, h] * pos7[r, c]   (pos_linear weight grad, K = 7).
+// CTA = 64 features x 128 rows: thread (h, row quarter) sums its 32 rows with 8 loads in flight, the four quarters meet
+// in shared memory and one thread per feature issues the 7 atomics.
 __global__ void __launch_bounds__(256)
 pos_linear_wgrad_kernel(const bf16* __restrict__ dp, const float* __restrict__ pos7,
-                        float* __restrict__ dW, int n, int H, int rows_per_block) {
+                        float* __restrict__ dW, int n, int H) {
     pdl_sync();
-    const int h = blockIdx.x * blockDim.x + threadIdx.x;
-    const int r0 = blockIdx.y * rows_per_block;
-    const int r1 = min(n, r0 + rows_per_block);
-    __shared__ float sp[64][8];
+    const int hl = threadIdx.x & 63, sub = threadIdx.x >> 6;
+    const int h = blockIdx.x * 64 + hl;
+    const int r0 = blockIdx.y * 128;
+    const int cnt = min(128, n - r0);
+    __shared__ float sp[128][8];
+    __shared__ float red[3][64][7];
+    for (int i = threadIdx.x; i < 128 * 7; i += blockDim.x) {
+        const int rr = i / 7, c = i - rr * 7;
+        sp[rr][c] = rr < cnt ? pos7[(size_t)(r0 + rr) * 7 + c] : 0.f;
+    }
+    __syncthreads();
     float acc[7];
 #pragma unroll
     for (int c = 0; c < 7; ++c) acc[c] = 0.f;
-    for (int rb = r0; rb < r1; rb += 64) {
-        __syncthreads();
-        for (int i = threadIdx.x; i < 64 * 7; i += blockDim.x) {
-            const int rr = i / 7, c = i - rr * 7;
-            sp[rr][c] = (rb + rr < r1) ? pos7[(size_t)(rb + rr) * 7 + c] : 0.f;
-        }
-        __syncthreads();
-        if (h < H) {
-            const int cnt = min(64, r1 - rb);
-            for (int rr = 0; rr < cnt; ++rr) {
-                const float v = __bfloat162float(dp[(size_t)(rb + rr) * H + h]);
+    if (h < H) {
 #pragma unroll
-                for (int c = 0; c < 7; ++c) acc[c] = fmaf(v, sp[rr][c], acc[c]);
+        for (int g = 0; g < 4; ++g) {
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int rr = sub * 32 + g * 8 + u;
+                v[u] = rr < cnt ? __bfloat162float(dp[(size_t)(r0 + rr) * H + h]) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int rr = sub * 32 + g * 8 + u;
+#pragma unroll
+                for (int c = 0; c < 7; ++c) acc[c] = fmaf(v[u], sp[rr][c], acc[c]);
             }
         }
     }
-    if (h < H)
+    if (sub > 0)
 #pragma unroll
-        for (int c = 0; c < 7; ++c) atomicAdd(dW + (size_t)h * 7 + c, acc[c]);
+        for (int c = 0; c < 7; ++c) red[sub - 1][hl][c] = acc[c];
+    __syncthreads();
+    if (sub == 0 && h < H)
+#pragma unroll
+        for (int c = 0; c < 7; ++c)
+            atomicAdd(dW + (size_t)h * 7 + c, acc[c] + red[0][hl][c] + red[1][hl][c] + red[2][hl][c]);
 }
 
 static DropoutCfg make_drop(const b200u_dropout_t* d) {
@@ -370,7 +453,19 @@ extern "C" int b200u_img_embed_fwd(const float* a, const float* pos7, const floa
     if (n == 0) return B200U_OK;
     DropoutCfg dc = make_drop(drop);
     B200U_CHECK_ARG(dc.thresh16 == 0 || dc.seed_ptr, "img_embed_fwd: dropout needs seed_ptr");
-    launch_k(img_embed_fwd_kernel, dim3((n + 7) / 8), dim3(256), 0, stream, a, pos7, Wpos, bpos, type_ids, type, g_img, b_img, g_pos, b_pos, g, b, (bf16*)out, p_out, s_out, stats_out, n, H, eps, dc);
+    const size_t smem = (size_t)16 * H * sizeof(float);
+    {
+        static std::mutex mu;
+        static size_t set_for[64] = {};
+        int dev = 0;
+        B200U_CHECK_CUDA(cudaGetDevice(&dev));
+        std::lock_guard<std::mutex> lock(mu);
+        if (dev >= 0 && dev < 64 && smem > set_for[dev]) {
+            B200U_CHECK_CUDA(cudaFuncSetAttribute(img_embed_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            set_for[dev] = smem;
+        }
+    }
+    launch_k(img_embed_fwd_kernel, dim3((n + 7) / 8), dim3(256), smem, stream, a, pos7, Wpos, bpos, type_ids, type, g_img, b_img, g_pos, b_pos, g, b, (bf16*)out, p_out, s_out, stats_out, n, H, eps, dc);
     B200U_CHECK_LAUNCH("img_embed_fwd");
     return B200U_OK;
 }
@@ -379,9 +474,12 @@ extern "C" int b200u_embedding_scatter_add(const void* d, const long long* ids, 
                                            int T, long long const_id, float* table_grad, int n, int H,
                                            long long padding_idx, b200u_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
-    B200U_CHECK_ARG(d && table_grad && H % 8 == 0 && T > 0, "embedding_scatter_add: bad arguments");
+    B200U_CHECK_ARG(d && table_grad && H % 8 == 0 && T > 0 && n % T == 0, "embedding_scatter_add: bad arguments (n must be B * T)");
     if (n == 0) return B200U_OK;
-    launch_k(embedding_scatter_add_kernel, dim3((n + 7) / 8), dim3(256), 0, stream, (const bf16*)d, ids, ids_batch_stride, T, const_id, table_grad, n, H, padding_idx);
+    B200U_CHECK_ARG(((uintptr_t)table_grad & 15) == 0, "embedding_scatter_add: table_grad must be 16-byte aligned");
+    const int nchunk = (H + 255) / 256, nseg = (n / T + 7) / 8;
+    const long long warps = (long long)T * nseg * nchunk;
+    launch_k(embedding_scatter_add_kernel, dim3((unsigned)((warps + 1) / 2)), dim3(64), 0, stream, (const bf16*)d, ids, ids_batch_stride, T, const_id, table_grad, n, H, padding_idx, nchunk, nseg);
     B200U_CHECK_LAUNCH("embedding_scatter_add");
     return B200U_OK;
 }
@@ -406,9 +504,8 @@ extern "C" int b200u_pos_linear_wgrad(const void* dp, const float* pos7, float* 
     cudaStream_t stream = (cudaStream_t)stream_;
     B200U_CHECK_ARG(dp && pos7 && dW, "pos_linear_wgrad: null pointer");
     if (n == 0) return B200U_OK;
-    const int rows_per_block = 128;
-    dim3 grid((H + 255) / 256, (n + rows_per_block - 1) / rows_per_block);
-    launch_k(pos_linear_wgrad_kernel, dim3(grid), dim3(256), 0, stream, (const bf16*)dp, pos7, dW, n, H, rows_per_block);
+    dim3 grid((H + 63) / 64, (n + 127) / 128);
+    launch_k(pos_linear_wgrad_kernel, dim3(grid), dim3(256), 0, stream, (const bf16*)dp, pos7, dW, n, H);
     B200U_CHECK_LAUNCH("pos_linear_wgrad");
     return B200U_OK;
 }

@@ -144,6 +144,9 @@ class TrainStep(object):
         self._ids_stream = None
         self._ids_event = None
         self._sumsq_done_from = None
+        self._sumsq_stream = None
+        self._sumsq_on_side = False
+        self.early_sumsq = os.environ.get("B200U_EARLY_SUMSQ", "1") != "0"
 
         # one flat store for the whole MemeUniter (UNITER + classification head)
         store = FlatStore(model)
@@ -203,6 +206,39 @@ class TrainStep(object):
         # enqueued: its bucket is final for this optimizer step, start the all-reduce now
         self.comm.reduce_bucket(layer_idx + 1)
 
+    def _on_layer_done_local(self, layer_idx):
+        """Single replica: the layer's gradient range is final once its backward is enqueued, so its share of
+        the clipping norm is taken NOW on a side stream (an HBM-bound read that co-resides with the next
+        layer's tensor-core GEMMs) instead of as one 340 MB pass in front of the optimizer; optimizer_step
+        only adds the embedding range. Layers finish in descending order, so the summed range stays one
+        suffix [_sumsq_done_from, n) of the flat gradient."""
+        lo, hi = self.buckets[layer_idx + 1]
+        cur = torch.cuda.current_stream()
+        if self._sumsq_stream is None:
+            self._sumsq_stream = torch.cuda.Stream()
+        if self._sumsq_done_from is None:
+            self.sumsq.zero_()
+            if hi != self.store.grad.numel():
+                return      # not the last bucket first: keep the one-pass path
+        elif hi != self._sumsq_done_from:
+            return
+        s = self._sumsq_stream
+        s.wait_stream(cur)
+        with torch.cuda.stream(s):
+            ops._call("b200u_grad_sumsq", P(self.store.grad[lo:hi]), C.c_size_t(hi - lo), P(self.sumsq), None,
+                      C.c_size_t(0), C.c_size_t(0))
+        self._sumsq_done_from = lo
+        self._sumsq_on_side = True
+
+    def _layer_cb(self, final):
+        """Backward hook for the encoder layers of a pass whose gradients are final (`final`): bucket all-reduce
+        in data parallel, early norm share on a single replica."""
+        if not final:
+            return None
+        if self.world > 1:
+            return self._on_layer_done if self.overlap_comm else None
+        return self._on_layer_done_local if (self.early_sumsq and self.store.grad.is_cuda) else None
+
     # ------------------------------------------------------------------ one micro-batch
     def _forward_loss(self, batch, last, first=True):
         """Forward + loss of one micro-batch on the current stream. Returns the state `_backward` needs.
@@ -214,7 +250,7 @@ class TrainStep(object):
         comm = self.world > 1 and last
         # the layer hooks are registered during the forward (they capture the callback), so it is only
         # set around this call
-        self.um._layer_grad_ready_cb = self._on_layer_done if (comm and self.overlap_comm) else None
+        self.um._layer_grad_ready_cb = self._layer_cb(last)
         # data parallel: EVERY micro-batch of the window hands its touched word-embedding rows over instead of
         # scattering them into the dense table; they are exchanged together after the last backward
         sparse = (self.world > 1 and self.overlap_comm and self.sparse_word and self.word_slice is not None)
@@ -353,7 +389,7 @@ class TrainStep(object):
                   img_pos_feat=cat["img_pos_feat"], attention_mask=cat["attn_mask"],
                   gather_index=cat["gather_index"], output_all_encoded_layers=False)
         comm = self.world > 1
-        self.um._layer_grad_ready_cb = self._on_layer_done if (comm and self.overlap_comm) else None
+        self.um._layer_grad_ready_cb = self._layer_cb(True)
         sparse = (comm and self.overlap_comm and self.sparse_word and self.word_slice is not None)
         if sparse:
             self._word_rows = []
@@ -435,6 +471,9 @@ class TrainStep(object):
         g16, lo16, hi16 = self.comm.bf16_range()
         if self._sumsq_done_from is not None:
             # the layer range was summed early: add the embedding range [0, lo16) (fp32)
+            if self._sumsq_on_side:
+                torch.cuda.current_stream().wait_stream(self._sumsq_stream)
+                self._sumsq_on_side = False
             ops._call("b200u_grad_sumsq", P(g), C.c_size_t(self._sumsq_done_from), P(self.sumsq), None,
                       C.c_size_t(0), C.c_size_t(0))
             self._sumsq_done_from = None

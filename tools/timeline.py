@@ -29,6 +29,11 @@ dev = torch.device("cuda", lrank)
 if world > 1:
     os.environ.setdefault("NCCL_MAX_CTAS", os.environ.get("TL_NCCL_CTAS", "16"))
     torch.distributed.init_process_group("nccl", device_id=dev)
+if "--no-pdl" in sys.argv:
+    # without programmatic dependent launch a kernel's CUPTI duration is its own run time (with PDL it includes the
+    # wait for its predecessor): use this mode to read per-kernel times, the default to read the real schedule
+    from meme_challenge_b200 import _lib
+    _lib.lib().b200u_set_pdl(0)
 torch.manual_seed(0)
 cfg = UniterConfig.from_dict(BASE)
 model = MemeUniter(UniterModel(cfg, 2048), BASE["hidden_size"], 1).to(dev).train()
