@@ -278,7 +278,7 @@ def _measure_finetune(args, model_cfg, window, rank, world, dev, host, devb, L_)
     ts = TrainStep(model, lr=3e-5, weight_decay=1e-3, gradient_accumulation=ACCUM, max_grad_norm=5.0, pos_wt=1.8,
                    overlap_comm=True, comm_sm_reserve=args.comm_sm_reserve if world > 1 else 0,
                    fuse_window=(window == "fused"),
-                   comm_dtype=(torch.bfloat16 if args.comm_dtype == "bf16" else None))
+                   comm_dtype=(torch.bfloat16 if args.comm_dtype == "bf16" else None), comm_impl=args.dp_impl)
     n_sets = len(devb) // ACCUM
 
     def barrier():
@@ -370,7 +370,8 @@ def _measure_finetune(args, model_cfg, window, rank, world, dev, host, devb, L_)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, ms_e2e = t.tolist()
     res = dict(ms=ms, ms_e2e=ms_e2e, clocks=clocks, last_loss=last_loss, h2d_bytes=h2d_bytes, use_graph=use_graph,
-               dp_mode=dp_mode, launches_per_step=int(launches_per_step), n_params=n_params)
+               dp_mode=dp_mode, launches_per_step=int(launches_per_step), n_params=n_params,
+               dp_impl=("ce" if ts.comm.peer is not None else "nccl"))
     if world > 1:
         # A captured CUDA graph holds NCCL kernels of this communicator: drop it before the process group.
         torch.cuda.synchronize()
@@ -538,6 +539,7 @@ def run_b200(args, rank, world, local_rank):
                            "window_other": other,
                            "cuda_graph": main["use_graph"], "dp_mode": main["dp_mode"] if world > 1 else None,
                            "grad_comm_dtype": args.comm_dtype if world > 1 else None,
+                           "grad_comm_impl": main.get("dp_impl") if world > 1 else None,
                            "nccl_max_ctas": args.nccl_max_ctas if world > 1 else None,
                            "comm_sm_reserve": args.comm_sm_reserve if world > 1 else None,
                            "l2": "per-step working set (saved activations + fp32 params/grads/Adam state + bf16 weights, "
@@ -578,6 +580,9 @@ def main():
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--dp-mode", default="auto", choices=["auto", "graph-overlap", "graph", "eager"],
                     help="N > 1: how the data-parallel step is launched (auto = first mode that captures)")
+    ap.add_argument("--dp-impl", default="auto", choices=["auto", "ce", "nccl"],
+                    help="N > 1, bf16 buckets: 'ce' = two-shot all-reduce with the copy engines over symmetric memory "
+                         "(no collective kernels on the SMs), 'nccl' = NCCL ring all-reduce, 'auto' = ce where available")
     ap.add_argument("--comm-dtype", default="bf16", choices=["bf16", "fp32"],
                     help="N > 1: dtype of the encoder-layer gradient buckets on the wire (fp32 accumulation stays local)")
     ap.add_argument("--nccl-max-ctas", type=int, default=16,

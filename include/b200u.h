@@ -146,6 +146,13 @@ int b200u_colsum_accum(const void* x, int ldx, float* out, int M, int N, b200u_s
 int b200u_dgelu_mul(const void* dy, const void* u, void* out, size_t n, b200u_stream_t stream);
 /* y(bf16)[i] = x(f32)[i], n % 8 == 0: img_feat / weight shadow casts. */
 int b200u_cast_f32_to_bf16(const float* x, void* y, size_t n, b200u_stream_t stream);
+/* dst(bf16)[i] = dst[i] + sum_k srcs[k][i] (fp32 accumulation, sources in the order given), n % 8 == 0,
+ * nsrc <= B200U_MAX_PEERS: the local reduce step of the data-parallel gradient exchange, where every rank
+ * sums its own slice of a bucket with the copies its peers pushed over NVLink with the copy engines
+ * (replaces the reduce half of the NCCL ring all-reduce behind torch DDP-style averaging,
+ * train_template.py:95-103 has no DP in the reference). */
+#define B200U_MAX_PEERS 15
+int b200u_slice_sum_bf16(void* dst, const void* const* srcs, int nsrc, size_t n, b200u_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * K1  gather_index concat (model/model.py:329-333): out[b,j,:] = cat(txt,img)[b, gather_index[b,j], :]

@@ -301,6 +301,28 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ x, bf16* __restri
     }
 }
 
+// dst[i] = bf16( f32(dst[i]) + sum_k f32(srcs[k][i]) ), sources added in the order given: the reduce step of the
+// copy-engine all-reduce of a gradient bucket slice (train.py PeerBuckets). n multiple of 8.
+struct SliceSrcs {
+    const bf16* p[B200U_MAX_PEERS];
+};
+__global__ void slice_sum_bf16_kernel(bf16* __restrict__ dst, SliceSrcs srcs, int nsrc, size_t nvec) {
+    pdl_sync();
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nvec;
+         i += (size_t)gridDim.x * blockDim.x) {
+        float acc[8];
+        load8(dst + i * 8, acc);
+#pragma unroll 4
+        for (int k = 0; k < nsrc; ++k) {
+            float f[8];
+            load8(srcs.p[k] + i * 8, f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] += f[j];
+        }
+        store8(dst + i * 8, acc);
+    }
+}
+
 // out = dy * gelu_erf'(u)  (backward of the standalone dense+GELU transforms of the heads)
 __global__ void dgelu_mul_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ u,
                                  bf16* __restrict__ out, size_t nvec) {
@@ -489,6 +511,26 @@ extern "C" int b200u_cast_f32_to_bf16(const float* x, void* y, size_t n, b200u_s
     if (grid > cap) grid = cap;
     launch_k(cast_f32_bf16_kernel, dim3((int)grid), dim3(256), 0, stream, x, (bf16*)y, nvec);
     B200U_CHECK_LAUNCH("cast_f32_to_bf16");
+    return B200U_OK;
+}
+
+extern "C" int b200u_slice_sum_bf16(void* dst, const void* const* srcs, int nsrc, size_t n, b200u_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    B200U_CHECK_ARG(dst && (srcs || nsrc == 0) && nsrc >= 0 && nsrc <= B200U_MAX_PEERS && n % 8 == 0 &&
+                        ((uintptr_t)dst & 15) == 0,
+                    "slice_sum_bf16: need <= %d 16-byte aligned sources and n %% 8 == 0", B200U_MAX_PEERS);
+    if (n == 0 || nsrc == 0) return B200U_OK;
+    SliceSrcs ss = {};
+    for (int k = 0; k < nsrc; ++k) {
+        B200U_CHECK_ARG(srcs[k] && ((uintptr_t)srcs[k] & 15) == 0, "slice_sum_bf16: source %d null or misaligned", k);
+        ss.p[k] = (const bf16*)srcs[k];
+    }
+    const size_t nvec = n / 8;
+    size_t grid = (nvec + 255) / 256;
+    const size_t cap = (size_t)num_sms() * 2;   // a side-stream kernel beside the backward GEMMs: keep it small
+    if (grid > cap) grid = cap;
+    launch_k(slice_sum_bf16_kernel, dim3((int)grid), dim3(256), 0, stream, (bf16*)dst, ss, nsrc, nvec);
+    B200U_CHECK_LAUNCH("slice_sum_bf16");
     return B200U_OK;
 }
 

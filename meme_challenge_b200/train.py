@@ -14,6 +14,7 @@ of nn.DataParallel's per-step parameter broadcast + gradient reduce, train_templ
 import ctypes as C
 import math
 import os
+import sys
 
 import torch
 
@@ -45,7 +46,7 @@ class GradBuckets(object):
     folded into the optimizer's gradient scale. Works on any backend (NCCL on GPUs, gloo in the
     CPU tests)."""
 
-    def __init__(self, entries, flat_grad, process_group=None, world=1, comm_dtype=None):
+    def __init__(self, entries, flat_grad, process_group=None, world=1, comm_dtype=None, comm_impl="auto"):
         self.grad = flat_grad
         self.pg = process_group
         self.world = world
@@ -68,10 +69,97 @@ class GradBuckets(object):
         self.segments = [(bounds[i], bounds[i + 1]) for i in range(len(bounds) - 1)]
         self.pending = []
         self.reduced = []
+        self._side_work = False
         self.sync = False  # True: blocking collectives on the current stream (graph-capturable)
+        self.peer = None       # copy-engine exchange state (see _setup_peer)
         if comm_dtype == torch.bfloat16 and world > 1 and len(self.segments) > 1:
             self.g16_lo = self.segments[1][0]
-            self.g16 = torch.zeros(n - self.g16_lo, device=flat_grad.device, dtype=torch.bfloat16)
+            want_ce = comm_impl in ("auto", "ce") and flat_grad.is_cuda and \
+                os.environ.get("B200U_DP_IMPL", "ce") != "nccl"
+            if want_ce:
+                try:
+                    self._setup_peer(n - self.g16_lo)
+                except Exception as e:   # no P2P / symmetric memory on this box: NCCL path
+                    if comm_impl == "ce":
+                        raise
+                    if torch.distributed.get_rank(process_group) == 0:
+                        print("b200u: symmetric-memory gradient exchange unavailable (%s); using NCCL all-reduce"
+                              % (str(e).splitlines()[0] if str(e) else type(e).__name__), file=sys.stderr)
+                    self.peer = None
+            if self.peer is None:
+                self.g16 = torch.zeros(n - self.g16_lo, device=flat_grad.device, dtype=torch.bfloat16)
+
+    # ------------------------------------------------------------------ copy-engine all-reduce over NVLink
+    def _setup_peer(self, n16):
+        """Two-shot all-reduce of the bf16 layer buckets WITHOUT collective kernels on the SMs.
+
+        An NCCL ring all-reduce keeps 8-32 CTAs resident for ~80 us per layer bucket while the backward's
+        persistent tcgen05 GEMMs want all 148 SMs: measured on 2 B200s it costs ~20 us of GEMM time per layer
+        (260 us per step, the whole data-parallel loss) whatever the channel count. Here the bucket lives in
+        symmetric memory (every rank maps every peer's buffer, NVSwitch gives all pairs full bandwidth) and
+        moves with the COPY ENGINES: rank r owns slice r of each bucket;
+          1. every rank pushes slice p of its bucket into peer p's staging area        (N-1 cudaMemcpyAsync P2P)
+          2. barrier; rank r sums its own slice with the N-1 staged copies             (b200u_slice_sum_bf16)
+          3. rank r pushes the reduced slice r into every peer's bucket                (N-1 cudaMemcpyAsync P2P)
+          4. barrier.
+        All of it is stream-ordered on the side stream that already does the fp32 -> bf16 cast, CUDA-graph
+        capturable (memcpy + kernel nodes), and deterministic: slice r is summed by one rank in a fixed order
+        and broadcast, so replicas stay bit-identical."""
+        import torch.distributed._symmetric_memory as symm_mem
+        dist = torch.distributed
+        W, dev = self.world, self.grad.device
+        rank = dist.get_rank(self.pg)
+        assert W - 1 <= 15, "b200u_slice_sum_bf16 takes at most 15 peers"
+        group = self.pg if self.pg is not None else dist.group.WORLD
+        # per bucket: slice length (multiple of 8 elements = 16 bytes) and staging offset
+        plan, stage_off = [], 0
+        for (lo, hi) in self.segments[1:]:
+            ln = hi - lo
+            sl = ((ln + W - 1) // W + 7) // 8 * 8
+            plan.append((lo - self.g16_lo, ln, sl, stage_off))
+            stage_off += W * sl
+        g16 = symm_mem.empty(n16, dtype=torch.bfloat16, device=dev)
+        stage = symm_mem.empty(max(stage_off, 8), dtype=torch.bfloat16, device=dev)
+        g16.zero_()
+        h_g = symm_mem.rendezvous(g16, group)
+        h_s = symm_mem.rendezvous(stage, group)
+        peers_g = [g16 if p == rank else h_g.get_buffer(p, (n16,), torch.bfloat16) for p in range(W)]
+        peers_s = [stage if p == rank else h_s.get_buffer(p, (stage.numel(),), torch.bfloat16) for p in range(W)]
+        self.g16 = g16
+        self.peer = dict(rank=rank, plan=plan, stage=stage, h=h_g, h_s=h_s, peers_g=peers_g, peers_s=peers_s)
+        torch.cuda.synchronize()
+        dist.barrier(group=self.pg)
+
+    def _peer_reduce(self, idx):
+        """Steps 1-4 of _setup_peer for bucket `idx` on the current (side) stream."""
+        pr = self.peer
+        W, r = self.world, pr["rank"]
+        off, ln, sl, soff = pr["plan"][idx - 1]
+
+        def sl_range(k):
+            a = min(k * sl, ln)
+            return a, min(a + sl, ln)
+
+        # 1. my copy of slice p -> peer p's staging slot r
+        for d in range(1, W):
+            p = (r + d) % W          # staggered targets: no two ranks hit the same peer at the same time
+            a, b = sl_range(p)
+            if b > a:
+                pr["peers_s"][p][soff + r * sl: soff + r * sl + (b - a)].copy_(self.g16[off + a: off + b], non_blocking=True)
+        pr["h"].barrier(channel=0)
+        # 2. reduce my slice (own value first, then peers in rank order)
+        a, b = sl_range(r)
+        if b > a:
+            n = b - a
+            n8 = (n + 7) // 8 * 8     # slices start 16-byte aligned; a ragged tail only exists on the last slice
+            srcs = [pr["stage"][soff + p * sl: soff + p * sl + n8] for p in range(W) if p != r]
+            arr = (C.c_void_p * len(srcs))(*[t.data_ptr() for t in srcs])
+            ops._call("b200u_slice_sum_bf16", P(self.g16[off + a: off + a + n8]), arr, len(srcs), C.c_size_t(n8))
+            # 3. reduced slice -> every peer's bucket
+            for d in range(1, W):
+                p = (r + d) % W
+                pr["peers_g"][p][off + a: off + b].copy_(self.g16[off + a: off + b], non_blocking=True)
+        pr["h"].barrier(channel=0)
 
     def bf16_range(self):
         """(buffer, lo, hi) of the gradient range the optimizer must read as bf16, or (None, 0, 0)."""
@@ -89,6 +177,9 @@ class GradBuckets(object):
             buf = self.g16[lo - self.g16_lo:hi - self.g16_lo]
             if self.sync or not self.grad.is_cuda:
                 ops.cast_f32_to_bf16(self.grad[lo:hi], buf)
+                if self.peer is not None:
+                    self._peer_reduce(idx)
+                    return
             else:
                 # the fp32 -> bf16 cast of the bucket leaves the backward's critical stream: it runs on a side
                 # stream forked here, and the all-reduce (NCCL stream) is ordered behind it
@@ -98,14 +189,25 @@ class GradBuckets(object):
                 self._cast_stream.wait_stream(cur)
                 with torch.cuda.stream(self._cast_stream):
                     ops.cast_f32_to_bf16(self.grad[lo:hi], buf)
-                    self.pending.append(torch.distributed.all_reduce(buf, group=self.pg, async_op=True))
+                    if self.peer is not None:
+                        self._peer_reduce(idx)
+                        self._side_work = True
+                    else:
+                        self.pending.append(torch.distributed.all_reduce(buf, group=self.pg, async_op=True))
                 return
         if self.sync:
             torch.distributed.all_reduce(buf, group=self.pg)
         else:
             self.pending.append(torch.distributed.all_reduce(buf, group=self.pg, async_op=True))
 
+    def join_side(self):
+        """Order the current stream behind the side stream's bucket exchanges issued so far."""
+        if self._side_work and self._cast_stream is not None:
+            torch.cuda.current_stream().wait_stream(self._cast_stream)
+            self._side_work = False
+
     def wait(self):
+        self.join_side()
         for w in self.pending:
             w.wait()
         self.pending = []
@@ -117,7 +219,7 @@ class TrainStep(object):
     def __init__(self, model, lr=3e-5, weight_decay=1e-3, betas=(0.9, 0.999), eps=1e-8,
                  gradient_accumulation=2, max_grad_norm=5.0, pos_wt=1.8, process_group=None,
                  overlap_comm=True, comm_sm_reserve=0, fuse_window=False, comm_dtype=torch.bfloat16,
-                 frozen=(), data_parallel=True):
+                 frozen=(), data_parallel=True, comm_impl="auto"):
         self.model = model
         self.um = model.uniter_model if hasattr(model, "uniter_model") else model.uniter
         self.accum = int(gradient_accumulation)
@@ -177,7 +279,7 @@ class TrainStep(object):
 
         # gradient buckets: index 0 = embeddings, 1.. = encoder layers (the last also holds pooler + head)
         self.comm = GradBuckets([(e[0], e[2]) for e in store.entries], store.grad, process_group, self.world,
-                                comm_dtype=comm_dtype)
+                                comm_dtype=comm_dtype, comm_impl=comm_impl)
         self.buckets = self.comm.segments
         self.comm.sync = not overlap_comm
         # Word-embedding gradient [vocab, H] (20 % of all parameters, produced LAST by every backward, so its
@@ -452,6 +554,7 @@ class TrainStep(object):
         instead of after them; optimizer_step then only adds the embedding range."""
         for h in layer_handles:
             h.wait()
+        self.comm.join_side()
         g16, lo16, hi16 = self.comm.bf16_range()
         if g16 is None:
             return

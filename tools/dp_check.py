@@ -31,12 +31,13 @@ def batch(seed):
     return d
 
 
-def run(sparse, graph, steps=2, comm_dtype=None, fused=False):
+def run(sparse, graph, steps=2, comm_dtype=None, fused=False, impl="auto"):
     torch.manual_seed(0)
     m = MemeUniter(UniterModel(UniterConfig.from_dict(cfg), IMG_DIM), cfg["hidden_size"], 1).to(dev).train()
     ts = TrainStep(m, lr=1e-3, weight_decay=1e-3, gradient_accumulation=2, max_grad_norm=5.0, pos_wt=1.8,
-                   comm_dtype=comm_dtype, fuse_window=fused)
+                   comm_dtype=comm_dtype, fuse_window=fused, comm_impl=impl)
     ts.sparse_word = sparse
+    used.append("ce" if ts.comm.peer is not None else "nccl")
     if graph:
         ts.capture([batch(100 + rank * 10), batch(101 + rank * 10)], warmup=0)
     for s in range(steps):
@@ -70,11 +71,14 @@ ref = single() if rank == 0 else None
 # fp32 gradient all-reduce: every variant must land on the single-process parameters (fp32 summation order
 # is the only difference); bf16 buckets: replicas still bit-identical, parameters within Adam's sensitivity
 # to a 2^-9 relative perturbation of the gradients (a near-zero gradient can flip the sign of a ~lr step)
-cases = [(None, sp, gr, False) for sp in (False, True) for gr in (False, True)]
-cases += [(None, True, True, True)]
-cases += [(torch.bfloat16, True, gr, fu) for gr in (False, True) for fu in (False, True)]
-for comm_dtype, sparse, graph, fused in cases:
-    p = run(sparse, graph, comm_dtype=comm_dtype, fused=fused)
+# bf16 buckets travel either with the copy engines over symmetric memory ("ce", the default where available) or as
+# NCCL all-reduces ("nccl")
+used = []
+cases = [(None, sp, gr, False, "auto") for sp in (False, True) for gr in (False, True)]
+cases += [(None, True, True, True, "auto")]
+cases += [(torch.bfloat16, True, gr, fu, impl) for impl in ("auto", "nccl") for gr in (False, True) for fu in (False, True)]
+for comm_dtype, sparse, graph, fused, impl in cases:
+    p = run(sparse, graph, comm_dtype=comm_dtype, fused=fused, impl=impl)
     gathered = [torch.empty_like(p) for _ in range(world)]
     dist.all_gather(gathered, p)
     same = all(torch.equal(gathered[0], g) for g in gathered)
@@ -82,8 +86,8 @@ for comm_dtype, sparse, graph, fused in cases:
         err = (p - ref).abs().max().item()
         mean_err = (p - ref).abs().mean().item()
         good = same and (err < 2e-4 if comm_dtype is None else (mean_err < 2e-5 and err < 5e-3))
-        print("comm=%s sparse=%d graph=%d fused=%d ranks_identical=%s max|p - single_process|=%.3e mean=%.3e %s" % (
-            "fp32" if comm_dtype is None else "bf16", sparse, graph, fused, same, err, mean_err, "ok" if good else "FAIL"),
+        print("comm=%s/%s sparse=%d graph=%d fused=%d ranks_identical=%s max|p - single_process|=%.3e mean=%.3e %s" % (
+            "fp32" if comm_dtype is None else "bf16", used[-1], sparse, graph, fused, same, err, mean_err, "ok" if good else "FAIL"),
             flush=True)
         ok = ok and good
 dist.barrier()
