@@ -369,6 +369,8 @@ def _measure_finetune(args, model_cfg, window, rank, world, dev, host, devb, L_)
         t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, ms_e2e = t.tolist()
+    from meme_challenge_b200.functional import check_input_errors
+    check_input_errors()   # no kernel of the timed steps was handed an out-of-range index
     res = dict(ms=ms, ms_e2e=ms_e2e, clocks=clocks, last_loss=last_loss, h2d_bytes=h2d_bytes, use_graph=use_graph,
                dp_mode=dp_mode, launches_per_step=int(launches_per_step), n_params=n_params,
                dp_impl=("ce" if ts.comm.peer is not None else "nccl"))

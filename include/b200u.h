@@ -29,6 +29,20 @@ typedef void* b200u_stream_t; /* cudaStream_t */
 enum { B200U_BF16 = 0, B200U_F32 = 1 };
 
 const char* b200u_last_error_string(void);
+/* Input-error word of the current device. The index-consuming kernels (embedding lookups and their scatter
+ * backward, the gather_index concat) never read or write out of bounds: an index outside its table makes them
+ * OR one of these bits into a 4-byte device word (the only memory the library owns) and use a safe substitute
+ * (row 0 / skip the row). b200u_input_errors synchronises the device, copies the word to *bits and optionally
+ * clears it; the reference raises IndexError / a device assert in the same situations (torch nn.Embedding,
+ * torch.gather at model/model.py:329-333). */
+enum {
+    B200U_ERR_WORD_ID = 1,
+    B200U_ERR_POS_ID = 2,
+    B200U_ERR_TYPE_ID = 4,
+    B200U_ERR_GATHER_INDEX = 8,
+    B200U_ERR_SCATTER_ID = 16
+};
+int b200u_input_errors(unsigned* bits /* host */, int reset);
 int b200u_version(void);
 /* Compiled SASS arch (100 for sm_100a) and SM count of the current device. */
 int b200u_device_info(int* sm_count, int* cc_major, int* cc_minor);
@@ -166,12 +180,15 @@ int b200u_gather_rows_bwd(const void* dout, const long long* gather_index, void*
 /* ------------------------------------------------------------------------------------------
  * K0  UniterTextEmbeddings.forward (model/model.py:232-245): LN(word[ids]+pos[pos_ids]+type[tids])
  * then dropout. position_ids may be [B,T] (pos_batch_stride = T) or [1,T] (stride 0);
- * type_ids NULL -> zeros. sum_out (f32 [B*T,H], pre-LN sum) and mean/rstd feed the backward. */
+ * type_ids NULL -> zeros. sum_out (f32 [B*T,H], pre-LN sum) and mean/rstd feed the backward.
+ * *_rows = row counts of the three tables: an id outside [0, rows) (nn.Embedding raises IndexError) sets
+ * B200U_ERR_* in the device's input-error word (b200u_input_errors) and row 0 is read instead. */
 int b200u_txt_embed_fwd(const long long* input_ids, const long long* position_ids,
                         int pos_batch_stride, const long long* type_ids, const float* word,
                         const float* pos, const float* type, const float* gamma, const float* beta,
                         void* out, float* sum_out, float* mean, float* rstd, int B, int T, int H,
-                        float eps, const b200u_dropout_t* drop, b200u_stream_t stream);
+                        int vocab_rows, int pos_rows, int type_rows, float eps,
+                        const b200u_dropout_t* drop, b200u_stream_t stream);
 /* K2  UniterImageEmbeddings.forward after img_linear (model/model.py:267-271):
  * LN(LN_img(a) + LN_pos(pos7·Wposᵀ+bpos) + type[type_ids]) then dropout. a = img_linear output
  * (f32 [n,H], from the GEMM). type_ids NULL -> ones (model/model.py:313-314).
@@ -180,17 +197,19 @@ int b200u_img_embed_fwd(const float* a, const float* pos7, const float* Wpos, co
                         const long long* type_ids, const float* type, const float* g_img,
                         const float* b_img, const float* g_pos, const float* b_pos, const float* g,
                         const float* b, void* out, float* p_out, float* s_out, float* stats_out,
-                        int n, int H, float eps, const b200u_dropout_t* drop, b200u_stream_t stream);
+                        int n, int H, int type_rows, float eps, const b200u_dropout_t* drop,
+                        b200u_stream_t stream);
 /* nn.Embedding backward: table_grad[id(r), :] += d[r, :] (bf16 rows, f32 atomics). ids NULL ->
- * every row uses const_id; ids are indexed [b*ids_batch_stride + t] with r = b*T + t. */
+ * every row uses const_id; ids are indexed [b*ids_batch_stride + t] with r = b*T + t (n = B*T). Rows whose id
+ * is outside [0, rows) are skipped and flagged (B200U_ERR_SCATTER_ID): nothing is ever added outside the table. */
 int b200u_embedding_scatter_add(const void* d, const long long* ids, int ids_batch_stride, int T,
                                 long long const_id, float* table_grad, int n, int H,
-                                long long padding_idx, b200u_stream_t stream);
+                                long long padding_idx, long long rows, b200u_stream_t stream);
 /* Deterministic (atomic-free) form for rows sorted by id: ids_sorted ascending, perm[p] = source row of
  * sorted entry p. One read-modify-write per distinct id, rows of a run added in sorted order, so equal
  * inputs give bit-identical tables (data-parallel exchange of the touched word-embedding rows). */
 int b200u_embedding_segment_add(const void* d, const long long* ids_sorted, const long long* perm,
-                                float* table_grad, int n, int H, long long padding_idx,
+                                float* table_grad, int n, int H, long long padding_idx, long long rows,
                                 b200u_stream_t stream);
 /* pos_linear weight gradient: dW[h,c] += sum_r dp[r,h] * pos7[r,c]. */
 int b200u_pos_linear_wgrad(const void* dp, const float* pos7, float* dW, int n, int H,

@@ -75,15 +75,22 @@ txt_embed_fwd_kernel(const long long* __restrict__ ids, const long long* __restr
                      const float* __restrict__ type, const float* __restrict__ gamma,
                      const float* __restrict__ beta, bf16* __restrict__ out, float* __restrict__ sum_out,
                      float* __restrict__ mean_out, float* __restrict__ rstd_out, int n, int T, int H,
+                     int vocab_rows, int pos_rows, int type_rows, unsigned* __restrict__ err,
                      float eps, DropoutCfg drop) {
     pdl_sync();
     const int lane = threadIdx.x & 31;
     const int tok = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (tok >= n) return;
     const int b = tok / T, t = tok - b * T;
-    const long long wid = ids[tok];
-    const long long pid = pos_ids[(size_t)b * pos_batch_stride + t];
-    const long long tid = type_ids ? type_ids[tok] : 0;
+    long long wid = ids[tok];
+    long long pid = pos_ids[(size_t)b * pos_batch_stride + t];
+    long long tid = type_ids ? type_ids[tok] : 0;
+    // out-of-range ids (nn.Embedding raises): flag them and read row 0 instead of out of bounds
+    unsigned bad = 0;
+    if (wid < 0 || wid >= vocab_rows) { bad |= ERR_WORD_ID; wid = 0; }
+    if (pid < 0 || pid >= pos_rows) { bad |= ERR_POS_ID; pid = 0; }
+    if (tid < 0 || tid >= type_rows) { bad |= ERR_TYPE_ID; tid = 0; }
+    if (bad && lane == 0 && err) atomicOr(err, bad);
     const int nv = H >> 3;
     float x[EMB_MAXV][8];
 #pragma unroll
@@ -130,7 +137,8 @@ img_embed_fwd_kernel(const float* __restrict__ a, const float* __restrict__ pos7
                      const float* __restrict__ g_pos, const float* __restrict__ b_pos,
                      const float* __restrict__ g, const float* __restrict__ be,
                      bf16* __restrict__ out, float* __restrict__ p_out, float* __restrict__ s_out,
-                     float* __restrict__ stats_out, int n, int H, float eps, DropoutCfg drop) {
+                     float* __restrict__ stats_out, int n, int H, int type_rows, unsigned* __restrict__ err,
+                     float eps, DropoutCfg drop) {
     pdl_sync();
     // Everything that does not depend on the row is staged once per CTA with 16-byte loads in ONE round trip:
     // pos_linear's weight [H][7] (a lane's 8 consecutive features are 56 contiguous floats) and bias, the three
@@ -149,6 +157,10 @@ img_embed_fwd_kernel(const float* __restrict__ a, const float* __restrict__ pos7
 #pragma unroll
         for (int c = 0; c < 7; ++c) pf[c] = pos7[(size_t)row * 7 + c];
         if (type_ids) tid = type_ids[row];
+        if (tid < 0 || tid >= type_rows) {
+            if (lane == 0 && err) atomicOr(err, (unsigned)ERR_TYPE_ID);
+            tid = 0;
+        }
 #pragma unroll
         for (int i = 0; i < EMB_MAXV; ++i)
             if (lane + 32 * i < nv) ld8f(a + (size_t)row * H + (lane + 32 * i) * 8, xa[i]);
@@ -240,7 +252,8 @@ img_embed_fwd_kernel(const float* __restrict__ a, const float* __restrict__ pos7
 __global__ void __launch_bounds__(64)
 embedding_scatter_add_kernel(const bf16* __restrict__ d, const long long* __restrict__ ids,
                              int ids_batch_stride, int T, long long const_id, float* __restrict__ table_grad,
-                             int n, int H, long long padding_idx, int nchunk, int nseg) {
+                             int n, int H, long long padding_idx, int nchunk, int nseg, long long rows,
+                             unsigned* __restrict__ err) {
     pdl_sync();
     const int lane = threadIdx.x & 31;
     int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -255,6 +268,10 @@ embedding_scatter_add_kernel(const bf16* __restrict__ d, const long long* __rest
     const int bb = b0 + (lane & 7);
     long long my_id = const_id;
     if (ids && bb < B) my_id = ids[(size_t)bb * ids_batch_stride + t];
+    if (my_id != padding_idx && (my_id < 0 || my_id >= rows)) {   // never add outside the table: flag and skip the row
+        if (err && c == 0) atomicOr(err, (unsigned)ERR_SCATTER_ID);
+        my_id = padding_idx;
+    }
     uint4 u[8];
 #pragma unroll
     for (int r = 0; r < 8; ++r)
@@ -305,7 +322,8 @@ embedding_scatter_add_kernel(const bf16* __restrict__ d, const long long* __rest
 __global__ void __launch_bounds__(256)
 embedding_segment_add_kernel(const bf16* __restrict__ d, const long long* __restrict__ ids_sorted,
                              const long long* __restrict__ perm, float* __restrict__ table_grad, int n,
-                             int H, long long padding_idx, int nchunk) {
+                             int H, long long padding_idx, int nchunk, long long rows,
+                             unsigned* __restrict__ err) {
     pdl_sync();
     const int lane = threadIdx.x & 31;
     const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -313,6 +331,10 @@ embedding_segment_add_kernel(const bf16* __restrict__ d, const long long* __rest
     if (p >= n) return;
     const long long id = ids_sorted[p];
     if (id == padding_idx) return;
+    if (id < 0 || id >= rows) {
+        if (err && lane == 0 && c == 0) atomicOr(err, (unsigned)ERR_SCATTER_ID);
+        return;
+    }
     if (p > 0 && ids_sorted[p - 1] == id) return;  // not the first entry of its run
     const int col = c * 256 + lane * 8;
     const bool active = col < H;
@@ -427,8 +449,9 @@ extern "C" int b200u_txt_embed_fwd(const long long* input_ids, const long long* 
                                    int pos_batch_stride, const long long* type_ids, const float* word,
                                    const float* pos, const float* type, const float* gamma,
                                    const float* beta, void* out, float* sum_out, float* mean,
-                                   float* rstd, int B, int T, int H, float eps,
-                                   const b200u_dropout_t* drop, b200u_stream_t stream_) {
+                                   float* rstd, int B, int T, int H, int vocab_rows, int pos_rows,
+                                   int type_rows, float eps, const b200u_dropout_t* drop,
+                                   b200u_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     CHECK_H(H);
     B200U_CHECK_ARG(input_ids && position_ids && word && pos && type && gamma && beta && out, "txt_embed_fwd: null pointer");
@@ -436,7 +459,7 @@ extern "C" int b200u_txt_embed_fwd(const long long* input_ids, const long long* 
     if (n == 0) return B200U_OK;
     DropoutCfg dc = make_drop(drop);
     B200U_CHECK_ARG(dc.thresh16 == 0 || dc.seed_ptr, "txt_embed_fwd: dropout needs seed_ptr");
-    launch_k(txt_embed_fwd_kernel, dim3((n + 7) / 8), dim3(256), 0, stream, input_ids, position_ids, pos_batch_stride, type_ids, word, pos, type, gamma, beta, (bf16*)out, sum_out, mean, rstd, n, T, H, eps, dc);
+    launch_k(txt_embed_fwd_kernel, dim3((n + 7) / 8), dim3(256), 0, stream, input_ids, position_ids, pos_batch_stride, type_ids, word, pos, type, gamma, beta, (bf16*)out, sum_out, mean, rstd, n, T, H, vocab_rows, pos_rows, type_rows, dev_err_ptr(), eps, dc);
     B200U_CHECK_LAUNCH("txt_embed_fwd");
     return B200U_OK;
 }
@@ -446,10 +469,12 @@ extern "C" int b200u_img_embed_fwd(const float* a, const float* pos7, const floa
                                    const float* g_img, const float* b_img, const float* g_pos,
                                    const float* b_pos, const float* g, const float* b, void* out,
                                    float* p_out, float* s_out, float* stats_out, int n, int H,
-                                   float eps, const b200u_dropout_t* drop, b200u_stream_t stream_) {
+                                   int type_rows, float eps, const b200u_dropout_t* drop,
+                                   b200u_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     CHECK_H(H);
     B200U_CHECK_ARG(a && pos7 && Wpos && bpos && type && g_img && b_img && g_pos && b_pos && g && b && out, "img_embed_fwd: null pointer");
+    B200U_CHECK_ARG(type_rows >= 2, "img_embed_fwd: the token-type table needs >= 2 rows (image regions default to type 1)");
     if (n == 0) return B200U_OK;
     DropoutCfg dc = make_drop(drop);
     B200U_CHECK_ARG(dc.thresh16 == 0 || dc.seed_ptr, "img_embed_fwd: dropout needs seed_ptr");
@@ -465,28 +490,28 @@ extern "C" int b200u_img_embed_fwd(const float* a, const float* pos7, const floa
             set_for[dev] = smem;
         }
     }
-    launch_k(img_embed_fwd_kernel, dim3((n + 7) / 8), dim3(256), smem, stream, a, pos7, Wpos, bpos, type_ids, type, g_img, b_img, g_pos, b_pos, g, b, (bf16*)out, p_out, s_out, stats_out, n, H, eps, dc);
+    launch_k(img_embed_fwd_kernel, dim3((n + 7) / 8), dim3(256), smem, stream, a, pos7, Wpos, bpos, type_ids, type, g_img, b_img, g_pos, b_pos, g, b, (bf16*)out, p_out, s_out, stats_out, n, H, type_rows, dev_err_ptr(), eps, dc);
     B200U_CHECK_LAUNCH("img_embed_fwd");
     return B200U_OK;
 }
 
 extern "C" int b200u_embedding_scatter_add(const void* d, const long long* ids, int ids_batch_stride,
                                            int T, long long const_id, float* table_grad, int n, int H,
-                                           long long padding_idx, b200u_stream_t stream_) {
+                                           long long padding_idx, long long rows, b200u_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     B200U_CHECK_ARG(d && table_grad && H % 8 == 0 && T > 0 && n % T == 0, "embedding_scatter_add: bad arguments (n must be B * T)");
     if (n == 0) return B200U_OK;
     B200U_CHECK_ARG(((uintptr_t)table_grad & 15) == 0, "embedding_scatter_add: table_grad must be 16-byte aligned");
     const int nchunk = (H + 255) / 256, nseg = (n / T + 7) / 8;
     const long long warps = (long long)T * nseg * nchunk;
-    launch_k(embedding_scatter_add_kernel, dim3((unsigned)((warps + 1) / 2)), dim3(64), 0, stream, (const bf16*)d, ids, ids_batch_stride, T, const_id, table_grad, n, H, padding_idx, nchunk, nseg);
+    launch_k(embedding_scatter_add_kernel, dim3((unsigned)((warps + 1) / 2)), dim3(64), 0, stream, (const bf16*)d, ids, ids_batch_stride, T, const_id, table_grad, n, H, padding_idx, nchunk, nseg, rows, dev_err_ptr());
     B200U_CHECK_LAUNCH("embedding_scatter_add");
     return B200U_OK;
 }
 
 extern "C" int b200u_embedding_segment_add(const void* d, const long long* ids_sorted, const long long* perm,
                                            float* table_grad, int n, int H, long long padding_idx,
-                                           b200u_stream_t stream_) {
+                                           long long rows, b200u_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     B200U_CHECK_ARG(d && ids_sorted && perm && table_grad, "embedding_segment_add: null pointer");
     B200U_CHECK_ARG(H % 8 == 0, "embedding_segment_add: H must be a multiple of 8");
@@ -494,7 +519,7 @@ extern "C" int b200u_embedding_segment_add(const void* d, const long long* ids_s
     const int nchunk = (H + 255) / 256;
     const long long warps = (long long)n * nchunk;
     launch_k(embedding_segment_add_kernel, dim3((unsigned)((warps + 7) / 8)), dim3(256), 0, stream, (const bf16*)d,
-             ids_sorted, perm, table_grad, n, H, padding_idx, nchunk);
+             ids_sorted, perm, table_grad, n, H, padding_idx, nchunk, rows, dev_err_ptr());
     B200U_CHECK_LAUNCH("embedding_segment_add_kernel");
     return B200U_OK;
 }

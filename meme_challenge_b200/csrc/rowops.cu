@@ -346,13 +346,17 @@ __global__ void dgelu_mul_kernel(const bf16* __restrict__ dy, const bf16* __rest
 __global__ void __launch_bounds__(256)
 gather_rows_kernel(const bf16* __restrict__ txt, const bf16* __restrict__ img,
                    const long long* __restrict__ gidx, bf16* __restrict__ out, int B, int T, int R,
-                   int L, int H) {
+                   int L, int H, unsigned* __restrict__ err) {
     pdl_sync();
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= B * L) return;
     const int b = row / L;
-    const long long idx = gidx[row];
+    long long idx = gidx[row];
+    if (idx < 0 || idx >= T + R) {   // torch.gather raises: flag it and read row 0 instead of out of bounds
+        if (lane == 0 && err) atomicOr(err, (unsigned)ERR_GATHER_INDEX);
+        idx = 0;
+    }
     const bf16* src = (idx < T) ? txt + ((size_t)b * T + idx) * H : img + ((size_t)b * R + (idx - T)) * H;
     const uint4* s4 = reinterpret_cast<const uint4*>(src);
     uint4* d4 = reinterpret_cast<uint4*>(out + (size_t)row * H);
@@ -552,7 +556,7 @@ extern "C" int b200u_gather_rows(const void* txt, const void* img, const long lo
     cudaStream_t stream = (cudaStream_t)stream_;
     B200U_CHECK_ARG(txt && img && gather_index && out && H % 8 == 0, "gather_rows: bad arguments");
     if (B * L == 0) return B200U_OK;
-    launch_k(gather_rows_kernel, dim3((B * L + 7) / 8), dim3(256), 0, stream, (const bf16*)txt, (const bf16*)img, gather_index, (bf16*)out, B, T, R, L, H);
+    launch_k(gather_rows_kernel, dim3((B * L + 7) / 8), dim3(256), 0, stream, (const bf16*)txt, (const bf16*)img, gather_index, (bf16*)out, B, T, R, L, H, dev_err_ptr());
     B200U_CHECK_LAUNCH("gather_rows");
     return B200U_OK;
 }

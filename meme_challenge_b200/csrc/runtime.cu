@@ -2,6 +2,8 @@
 #include "../../include/b200u.h"
 #include "common.cuh"
 
+#include <mutex>
+
 #include <cudaTypedefs.h>
 #include <stdarg.h>
 #include <stdlib.h>
@@ -116,7 +118,35 @@ int make_tmap_3d(CUtensorMap* tm, const void* ptr, int batch, int rows, int cols
     return B200U_OK;
 }
 
+// Per-device 4-byte input-error word (the one allocation the library owns): kernels OR a bit into it when an index they
+// were handed is out of range, and substitute a safe value instead of reading or writing out of bounds.
+static std::mutex g_flag_mu;
+static unsigned* g_flag[64] = {};
+unsigned* dev_err_ptr() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    std::lock_guard<std::mutex> lock(g_flag_mu);
+    if (!g_flag[dev]) {
+        unsigned* p = nullptr;
+        if (cudaMalloc(&p, sizeof(unsigned)) != cudaSuccess) return nullptr;
+        cudaMemset(p, 0, sizeof(unsigned));
+        g_flag[dev] = p;
+    }
+    return g_flag[dev];
+}
+
 }  // namespace b200u
+
+extern "C" int b200u_input_errors(unsigned* bits, int reset) {
+    using namespace b200u;
+    B200U_CHECK_ARG(bits, "input_errors: null pointer");
+    unsigned* p = dev_err_ptr();
+    B200U_CHECK_ARG(p, "input_errors: no error word on this device");
+    B200U_CHECK_CUDA(cudaDeviceSynchronize());
+    B200U_CHECK_CUDA(cudaMemcpy(bits, p, sizeof(unsigned), cudaMemcpyDeviceToHost));
+    if (reset) B200U_CHECK_CUDA(cudaMemset(p, 0, sizeof(unsigned)));
+    return B200U_OK;
+}
 
 extern "C" const char* b200u_last_error_string(void) { return b200u::g_err; }
 

@@ -42,6 +42,8 @@ def predict(model, batches, pos_wt=1.0):
     probs = torch.cat(probs) if probs else torch.empty(0)
     labels = torch.cat(labels) if labels else None
     mean_loss = float(torch.stack(losses).mean().item()) if losses else None
+    if probs.is_cuda:
+        F_.check_input_errors()   # the host waits here anyway: surface out-of-range ids / gather indices
     return probs, labels, mean_loss, (torch.cat(ids) if ids else None)
 
 

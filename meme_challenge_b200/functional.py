@@ -228,6 +228,33 @@ def bert_layer_infer(x0, mask_add, layer, layer_idx, rt, saved_cache):
 
 
 # ------------------------------------------------------------------------------------------------
+def _ids64(t, name):
+    """Index tensors reach the kernels as contiguous int64 (they read `const long long*`); integer tensors of
+    another width are converted, anything else is rejected like nn.Embedding does."""
+    if t.dtype == torch.int64:
+        return t.contiguous()
+    if t.dtype in (torch.int32, torch.int16, torch.int8, torch.uint8):
+        return t.long().contiguous()
+    raise _lib.B200UError("%s must be an integer tensor, got %s" % (name, t.dtype))
+
+
+_ERR_BITS = ((1, "input_ids outside the word-embedding table"), (2, "position_ids outside the position table"),
+             (4, "token type ids outside the token-type table"), (8, "gather_index outside [0, T + R)"),
+             (16, "an embedding gradient row outside its table"))
+
+
+def check_input_errors(reset=True):
+    """Raise if any index-consuming kernel since the last check saw an out-of-range index (the kernels flag it and
+    substitute a safe row instead of reading or writing out of bounds; the reference raises IndexError / a device
+    assert). Synchronises the device: call it where the host waits anyway (after reading a loss, at evaluation end,
+    before a checkpoint)."""
+    bits = C.c_uint(0)
+    _lib.check(_lib.lib().b200u_input_errors(C.byref(bits), int(bool(reset))), "b200u_input_errors")
+    if bits.value:
+        raise _lib.B200UError("invalid indices reached the device: " +
+                              "; ".join(msg for bit, msg in _ERR_BITS if bits.value & bit))
+
+
 class TxtEmbedFn(torch.autograd.Function):
     """UniterTextEmbeddings.forward (model/model.py:232-245)."""
 
@@ -236,15 +263,16 @@ class TxtEmbedFn(torch.autograd.Function):
         B, T = input_ids.shape
         H = emb.word_embeddings.weight.shape[1]
         dev = input_ids.device
-        input_ids = input_ids.contiguous()
-        position_ids = position_ids.contiguous()
+        # the kernels read 64-bit ids (nn.Embedding also accepts int32): convert anything else
+        input_ids = _ids64(input_ids, "input_ids")
+        position_ids = _ids64(position_ids, "position_ids")
         if position_ids.dim() == 1:
             position_ids = position_ids.unsqueeze(0)
         if position_ids.shape[0] not in (1, B) or position_ids.shape[1] != T:
             raise _lib.B200UError("position_ids must be [B,T] or [1,T]")
         pos_stride = T if position_ids.shape[0] == B else 0
         if token_type_ids is not None:
-            token_type_ids = token_type_ids.contiguous()
+            token_type_ids = _ids64(token_type_ids, "token_type_ids")
         out = torch.empty(B, T, H, device=dev, dtype=torch.bfloat16)
         need = any(ctx.needs_input_grad)  # grad mode is off inside Function.forward
         sum_out = torch.empty(B * T, H, device=dev, dtype=torch.float32) if need else None
@@ -254,7 +282,9 @@ class TxtEmbedFn(torch.autograd.Function):
         ops._call("b200u_txt_embed_fwd", P(input_ids), P(position_ids), pos_stride, P(token_type_ids),
                   P(emb.word_embeddings.weight), P(emb.position_embeddings.weight),
                   P(emb.token_type_embeddings.weight), P(emb.LayerNorm.weight), P(emb.LayerNorm.bias),
-                  P(out), P(sum_out), P(mean), P(rstd), B, T, H, float(emb.LayerNorm.eps), C.byref(drop))
+                  P(out), P(sum_out), P(mean), P(rstd), B, T, H, emb.word_embeddings.weight.shape[0],
+                  emb.position_embeddings.weight.shape[0], emb.token_type_embeddings.weight.shape[0],
+                  float(emb.LayerNorm.eps), C.byref(drop))
         ctx.emb, ctx.rt, ctx.drop = emb, rt, drop
         ctx.ids = (input_ids, position_ids, pos_stride, token_type_ids)
         ctx.stats = (sum_out, mean, rstd)
@@ -279,15 +309,17 @@ class TxtEmbedFn(torch.autograd.Function):
             ctx.rt.sparse_word_cb(dx, input_ids.reshape(-1), -1 if pad is None else pad)
         else:
             ops._call("b200u_embedding_scatter_add", P(dx), P(input_ids), T, T, C.c_longlong(0),
-                      P(grad_buf(emb.word_embeddings.weight)), B * T, H, C.c_longlong(-1 if pad is None else pad))
+                      P(grad_buf(emb.word_embeddings.weight)), B * T, H, C.c_longlong(-1 if pad is None else pad),
+                      C.c_longlong(emb.word_embeddings.weight.shape[0]))
         ops._call("b200u_embedding_scatter_add", P(dx), P(position_ids), pos_stride, T, C.c_longlong(0),
-                  P(grad_buf(emb.position_embeddings.weight)), B * T, H, C.c_longlong(-1))
+                  P(grad_buf(emb.position_embeddings.weight)), B * T, H, C.c_longlong(-1),
+                  C.c_longlong(emb.position_embeddings.weight.shape[0]))
         tg = grad_buf(emb.token_type_embeddings.weight)
         if token_type_ids is None:
             ops.colsum_accum(dx, tg[0])
         else:
             ops._call("b200u_embedding_scatter_add", P(dx), P(token_type_ids), T, T, C.c_longlong(0), P(tg),
-                      B * T, H, C.c_longlong(-1))
+                      B * T, H, C.c_longlong(-1), C.c_longlong(tg.shape[0]))
         return None, None, None, None, None, None
 
 
@@ -315,7 +347,7 @@ class ImgEmbedFn(torch.autograd.Function):
         a = ops.gemm(feat16, w16, epilogue=EPI_STORE_F32, bias=iemb.img_linear.bias, impl=rt.gemm_impl)
         pos7 = img_pos_feat.contiguous().float().view(n, 7)
         if img_type_ids is not None:
-            img_type_ids = img_type_ids.contiguous()
+            img_type_ids = _ids64(img_type_ids, "img_type_ids")
         out = torch.empty(B, R, H, device=dev, dtype=torch.bfloat16)
         need = any(ctx.needs_input_grad)  # grad mode is off inside Function.forward
         p_out = torch.empty(n, H, device=dev, dtype=torch.float32) if need else None
@@ -325,7 +357,7 @@ class ImgEmbedFn(torch.autograd.Function):
         ops._call("b200u_img_embed_fwd", P(a), P(pos7), P(iemb.pos_linear.weight), P(iemb.pos_linear.bias),
                   P(img_type_ids), P(type_table), P(iemb.img_layer_norm.weight), P(iemb.img_layer_norm.bias),
                   P(iemb.pos_layer_norm.weight), P(iemb.pos_layer_norm.bias), P(iemb.LayerNorm.weight),
-                  P(iemb.LayerNorm.bias), P(out), P(p_out), P(s_out), P(stats), n, H,
+                  P(iemb.LayerNorm.bias), P(out), P(p_out), P(s_out), P(stats), n, H, type_table.shape[0],
                   float(iemb.LayerNorm.eps), C.byref(drop))
         ctx.iemb, ctx.rt, ctx.drop, ctx.type_table = iemb, rt, drop, type_table
         ctx.t = (feat16, a, pos7, p_out, s_out, stats, img_type_ids, img_masks)
@@ -348,7 +380,7 @@ class ImgEmbedFn(torch.autograd.Function):
             ops.colsum_accum(ds, tg[1])
         else:
             ops._call("b200u_embedding_scatter_add", P(ds), P(img_type_ids), R, R, C.c_longlong(0), P(tg), n, H,
-                      C.c_longlong(-1))
+                      C.c_longlong(-1), C.c_longlong(tg.shape[0]))
         # LN_img backward -> da (grad of img_linear output) + its bias grad
         da, _ = ops.layernorm_bwd(ds, a, stats[0], stats[1], iemb.img_layer_norm.weight,
                                   grad_buf(iemb.img_layer_norm.weight), grad_buf(iemb.img_layer_norm.bias),
@@ -366,7 +398,8 @@ class ImgEmbedFn(torch.autograd.Function):
             dfeat = ops.gemm(da, rt.store.w16(iemb.img_linear.weight), b_mn=True, impl=rt.gemm_impl)
             ids = img_masks.long().contiguous()
             ops._call("b200u_embedding_scatter_add", P(dfeat), P(ids), R, R, C.c_longlong(0),
-                      P(grad_buf(iemb.mask_embedding.weight)), n, D, C.c_longlong(0))
+                      P(grad_buf(iemb.mask_embedding.weight)), n, D, C.c_longlong(0),
+                      C.c_longlong(iemb.mask_embedding.weight.shape[0]))
         return None, None, None, None, None, None, None, None
 
 
@@ -375,7 +408,7 @@ class GatherFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, txt_emb, img_emb, gather_index):
-        gather_index = gather_index.contiguous()
+        gather_index = _ids64(gather_index, "gather_index")
         ctx.gi = gather_index
         ctx.TR = (txt_emb.shape[1], img_emb.shape[1])
         return ops.gather_rows(txt_emb.contiguous(), img_emb.contiguous(), gather_index)

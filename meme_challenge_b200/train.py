@@ -447,7 +447,7 @@ class TrainStep(object):
         tot = self.world * n
         assert self._ids_sorted.numel() == tot, "word-row exchange: ids of the window do not match its rows"
         ops._call("b200u_embedding_segment_add", P(all_rows), P(self._ids_sorted), P(self._ids_perm),
-                  P(self.store.grad[lo:hi]), tot, H, C.c_longlong(pad))
+                  P(self.store.grad[lo:hi]), tot, H, C.c_longlong(pad), C.c_longlong((hi - lo) // H))
 
     def micro_step(self, batch, last, first=True):
         return self._backward(self._forward_loss(batch, last, first))
@@ -597,6 +597,7 @@ class TrainStep(object):
         named_parameters() order, 'param_groups'), what the reference saves as `optimizer_state_dict`
         (utils/save.py:57-64) so a run can be resumed by either implementation."""
         step = int(self.step_t.item())
+        F_.check_input_errors()   # a checkpoint of a run that consumed invalid indices must not be written silently
         state = {}
         for i, (name, p) in enumerate(self.model.named_parameters()):
             off, cnt = self.store.index[id(p)]

@@ -307,9 +307,92 @@ def test_attention_dropout_is_consistent_between_fwd_and_bwd():
     assert abs(c[5, 7].float().item() - want.item()) < 2e-2
 
 
+def test_out_of_range_indices_are_flagged_not_dereferenced():
+    """nn.Embedding / torch.gather raise on an index outside the table (model/model.py:232-245, 329-333). The
+    kernels never dereference such an index: they flag it in the device's input-error word and substitute a safe
+    row; check_input_errors() then raises. int32 ids (which nn.Embedding accepts) are converted, not misread."""
+    _require_gpu()
+    from meme_challenge_b200 import functional as F_, ops
+    from meme_challenge_b200._lib import B200UError
+    F_.check_input_errors()          # start clean
+    b = O.synth_batch(2, 12, 10, seed=5, img_dim=IMG_DIM, vocab=TINY["vocab_size"], min_txt=2, min_bb=2)
+    m = _build(TINY, IMG_DIM).eval()
+    ref = m(**_kw(b)).detach().clone()
+    F_.check_input_errors()
+    # int32 ids give the same logits as int64
+    kw = _kw(b)
+    kw["input_ids"] = kw["input_ids"].int()
+    kw["position_ids"] = kw["position_ids"].int()
+    kw["gather_index"] = kw["gather_index"].int()
+    assert torch.equal(m(**kw).detach(), ref)
+    F_.check_input_errors()
+    # a word id beyond the vocabulary, forward AND backward: flagged, no fault, other gradients untouched
+    kw = _kw(b)
+    kw["input_ids"] = kw["input_ids"].clone()
+    kw["input_ids"][0, 1] = TINY["vocab_size"] + 7
+    m.train()
+    m(**kw).sum().backward()
+    with pytest.raises(B200UError, match="word-embedding"):
+        F_.check_input_errors()
+    F_.check_input_errors()          # the check cleared the word
+    # position id / gather index out of range
+    kw = _kw(b)
+    kw["position_ids"] = kw["position_ids"].clone()
+    kw["position_ids"][0, 0] = -3
+    m.eval()
+    m(**kw)
+    with pytest.raises(B200UError, match="position"):
+        F_.check_input_errors()
+    kw = _kw(b)
+    kw["gather_index"] = kw["gather_index"].clone()
+    kw["gather_index"][1, 2] = 10 ** 6
+    m(**kw)
+    with pytest.raises(B200UError, match="gather_index"):
+        F_.check_input_errors()
+    # float ids are rejected on the host
+    kw = _kw(b)
+    kw["input_ids"] = kw["input_ids"].float()
+    with pytest.raises(B200UError, match="integer"):
+        m(**kw)
+    # scatter backward with a bad id: the table's neighbours in the flat gradient stay untouched
+    d = torch.ones(4, 64, device=DEV).bfloat16()
+    guard = torch.zeros(3, 8, 64, device=DEV)
+    ids = torch.tensor([[0, 9, -1, 7]], device=DEV).t().contiguous()   # B = 4, T = 1; ids 9 and -1 are out of range
+    import ctypes as C
+    ops._call("b200u_embedding_scatter_add", ops.P(d), ops.P(ids), 1, 1, C.c_longlong(0), ops.P(guard[1]), 4, 64,
+              C.c_longlong(-100), C.c_longlong(8))
+    with pytest.raises(B200UError, match="gradient row"):
+        F_.check_input_errors()
+    assert guard[0].abs().sum().item() == 0 and guard[2].abs().sum().item() == 0
+    assert guard[1].sum().item() == 2 * 64      # rows 0 and 7 only
+
+
+@pytest.mark.parametrize("nsrc,n", [(1, 4096), (7, 8 * 1000 + 8), (15, 64)])
+def test_slice_sum_bf16_matches_fp32_sum_in_order(nsrc, n):
+    """b200u_slice_sum_bf16 (reduce step of the copy-engine gradient exchange): fp32 accumulation of the own slice
+    and the peers' copies in the order given, one rounding to bf16 -> bit-exact against the same sum in torch."""
+    _require_gpu()
+    import ctypes as C
+    from meme_challenge_b200 import ops
+    torch.manual_seed(nsrc)
+    own = torch.randn(n, device=DEV).bfloat16()
+    srcs = [torch.randn(n, device=DEV).bfloat16() for _ in range(nsrc)]
+    want = own.float()
+    for t in srcs:
+        want = want + t.float()
+    want = want.bfloat16()
+    arr = (C.c_void_p * nsrc)(*[t.data_ptr() for t in srcs])
+    ops._call("b200u_slice_sum_bf16", ops.P(own), arr, nsrc, C.c_size_t(n))
+    assert torch.equal(own.view(torch.int16), want.view(torch.int16))
+
+
 # ----------------------------------------------------------------------------------------------
 # whole model against the reference golden vectors and the oracle
 # ----------------------------------------------------------------------------------------------
+REL_L2_BOUND = 0.04       # matrices (weights, embedding tables); measured worst 0.029 (ragged C2 batch), median 0.012-0.020
+REL_L2_BOUND_VEC = 0.05   # bias and LayerNorm vectors; measured worst 0.026
+
+
 def _build(cfg_dict, img_dim, sd=None, seed=0):
     from meme_challenge_b200.model.meme_uniter import MemeUniter
     from meme_challenge_b200.model.model import UniterConfig, UniterModel
@@ -408,15 +491,26 @@ def test_base_c2_fwd_bwd_against_oracle(variable):
     ref_logits, ref_loss, sd = _oracle_run(m, BASE, b)
     assert (logits.detach().cpu() - ref_logits).abs().max() <= LOGIT_TOL
     assert abs(loss.item() - ref_loss.item()) <= LOSS_RTOL * abs(ref_loss.item())
-    bad = []
+    # per-tensor relative L2 error of every gradient against the fp32 oracle. The path computes in bf16 (operands
+    # rounded to 2^-9 relative, fp32 accumulation), so a tensor's error is a few bf16 ulps amplified by the depth of
+    # the chain behind it: bounds are REL_L2_BOUND for matrices and the looser REL_L2_BOUND_VEC for bias / LayerNorm
+    # vectors, whose few hundred entries are sums of strongly cancelling terms.
+    bad, worst = [], []
     for n, p in m.named_parameters():
         want = sd[n].grad
         if want is None or want.abs().max() < 1e-8:
             continue
-        c = _cos(p.grad.detach().cpu(), want)
-        if c < 0.98:
-            bad.append((n, c))
-    assert not bad, bad[:8]
+        got_g = p.grad.detach().cpu().float()
+        rel = ((got_g - want).norm() / want.norm()).item()
+        worst.append((rel, n))
+        bound = REL_L2_BOUND if want.dim() >= 2 else REL_L2_BOUND_VEC
+        if rel > bound or _cos(got_g, want) < 0.98:
+            bad.append((n, rel))
+    worst.sort(reverse=True)
+    if os.environ.get("B200U_PRINT_REL"):
+        print("per-tensor rel-L2 (worst 12):", [(round(r, 4), n) for r, n in worst[:12]])
+        print("median rel-L2:", worst[len(worst) // 2][0])
+    assert not bad, (bad[:8], worst[:3])
     # whole-gradient agreement
     names = [n for n, p in m.named_parameters() if sd[n].grad is not None]
     got = torch.cat([dict(m.named_parameters())[n].grad.detach().cpu().flatten() for n in names])

@@ -34,9 +34,9 @@ pos_ids = torch.arange(T, device=dev).unsqueeze(0).repeat(B, 1).contiguous()
 table = torch.zeros(28996, H, device=dev)
 ptab = torch.zeros(512, H, device=dev)
 res["scatter_add_word"] = _time_graph(lambda i: ops._call(
-    "b200u_embedding_scatter_add", P(d[i]), P(word_ids), T, T, C.c_longlong(0), P(table), B * T, H, C.c_longlong(0)))
+    "b200u_embedding_scatter_add", P(d[i]), P(word_ids), T, T, C.c_longlong(0), P(table), B * T, H, C.c_longlong(0), C.c_longlong(28996)))
 res["scatter_add_pos"] = _time_graph(lambda i: ops._call(
-    "b200u_embedding_scatter_add", P(d[i]), P(pos_ids), T, T, C.c_longlong(0), P(ptab), B * T, H, C.c_longlong(-1)))
+    "b200u_embedding_scatter_add", P(d[i]), P(pos_ids), T, T, C.c_longlong(0), P(ptab), B * T, H, C.c_longlong(-1), C.c_longlong(512)))
 
 # ---- image embedder forward
 n = B * R
@@ -51,7 +51,7 @@ stats = torch.empty(6, n, device=dev)
 drop = _lib.dropout_t(seed, 2, 0.1)
 res["img_embed_fwd"] = _time_graph(lambda i: ops._call(
     "b200u_img_embed_fwd", P(a[i]), P(pos7), P(Wp), P(bp), None, P(ty), P(ones), P(zeros), P(ones), P(zeros), P(ones),
-    P(zeros), P(out), P(p_out), P(s_out), P(stats), n, H, 1e-12, C.byref(drop)))
+    P(zeros), P(out), P(p_out), P(s_out), P(stats), n, H, 2, 1e-12, C.byref(drop)))
 dp = two(lambda: torch.randn(n, H, device=dev).bfloat16())
 dWp = torch.zeros(H, 7, device=dev)
 res["pos_linear_wgrad"] = _time_graph(lambda i: ops._call("b200u_pos_linear_wgrad", P(dp[i]), P(pos7), P(dWp), n, H))
