@@ -107,7 +107,15 @@ enum {
                                     exchange row statistics through distributed shared memory;
                                     ln_mean / ln_rstd (f32 [M]) are saved for the backward
                                     (model/layer.py:111-115,152-156)                                  */
-    B200U_EPI_COUNT = 10
+    B200U_EPI_CE_STATS = 10,     /* vocabulary GEMM fused with cross entropy, forward (BertLMPredictionHead decoder +
+                                    F.cross_entropy, model/layer.py:204-221, model/pretrain.py:97-98): the logits
+                                    acc + bias are never written; per (row, 128-column tile) the epilogue emits
+                                    ce_partial = (max, sum exp(x - max)) and ce_tlogit[row] = logit at ce_target[row].
+                                    K-major A and B only; b200u_ce_finish turns the partials into lse and loss   */
+    B200U_EPI_CE_GRAD = 11,      /* backward of the same: the logits are RECOMPUTED and
+                                    C(bf16)[m,n] = (exp(acc + bias - ce_lse[m]) - [n == ce_target[m]]) * ce_scale[m],
+                                    the operand of the decoder's dgrad / wgrad GEMMs                            */
+    B200U_EPI_COUNT = 12
 };
 
 typedef struct {
@@ -130,9 +138,18 @@ typedef struct {
     float* ln_mean;         /* f32 [M] or NULL */
     float* ln_rstd;         /* f32 [M] or NULL */
     float ln_eps;
+    const long long* ce_target; /* EPI_CE_STATS / EPI_CE_GRAD: i64 [M] target column of each row */
+    float* ce_partial;          /* EPI_CE_STATS: f32 [M][ceil(N/128)][2] (max, sum exp) per row and column tile */
+    float* ce_tlogit;           /* EPI_CE_STATS: f32 [M] logit at the target */
+    const float* ce_lse;        /* EPI_CE_GRAD: f32 [M] log-sum-exp of each row (from b200u_ce_finish) */
+    const float* ce_scale;      /* EPI_CE_GRAD: f32 [M] upstream gradient of each row's loss */
 } b200u_gemm_t;
 
 int b200u_gemm(const b200u_gemm_t* g, b200u_stream_t stream);
+/* Second half of EPI_CE_STATS: lse[m] = log sum_n exp(logit[m,n]) from the per-tile partials (n_tiles =
+ * ceil(N/128) of the GEMM) and loss[m] = lse[m] - tlogit[m] (F.cross_entropy(..., reduction='none')). */
+int b200u_ce_finish(const float* partial, const float* tlogit, float* lse, float* loss, int M, int n_tiles,
+                    b200u_stream_t stream);
 /* Bring-up aid: non-NULL -> every tcgen05 GEMM CTA writes 8 clock64() phase stamps (int64) to
  * device_ptr[cta*8 ..] (entry, setup done, TMA issued, first operands landed, MMAs issued,
  * accumulator ready, epilogue done, exit). NULL disables. */

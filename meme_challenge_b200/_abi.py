@@ -33,6 +33,7 @@ SIGNATURES = {
     "b200u_dgelu_mul": (_i, [_p, _p, _p, _sz, _p]),
     "b200u_cast_f32_to_bf16": (_i, [_p, _p, _sz, _p]),
     "b200u_slice_sum_bf16": (_i, [_p, _p, _i, _sz, _p]),
+    "b200u_ce_finish": (_i, [_p, _p, _p, _p, _i, _i, _p]),
     "b200u_gather_rows": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
     "b200u_gather_rows_bwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
     "b200u_txt_embed_fwd": (_i, [_p, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _f, _p, _p]),

@@ -38,12 +38,14 @@ class GemmT(C.Structure):
         ("colsum", C.c_void_p),
         ("ln_gamma", C.c_void_p), ("ln_beta", C.c_void_p), ("ln_mean", C.c_void_p), ("ln_rstd", C.c_void_p),
         ("ln_eps", C.c_float),
+        ("ce_target", C.c_void_p), ("ce_partial", C.c_void_p), ("ce_tlogit", C.c_void_p),
+        ("ce_lse", C.c_void_p), ("ce_scale", C.c_void_p),
     ]
 
 
 (EPI_STORE, EPI_BIAS_GELU, EPI_BIAS_DROP_RES, EPI_ADD, EPI_DGELU, EPI_ATOMIC_F32, EPI_STORE_F32,
- EPI_BIAS_GELU_DG, EPI_MUL, EPI_BIAS_DROP_RES_LN) = range(10)
-EPI_COUNT = 10
+ EPI_BIAS_GELU_DG, EPI_MUL, EPI_BIAS_DROP_RES_LN, EPI_CE_STATS, EPI_CE_GRAD) = range(12)
+EPI_COUNT = 12
 EPI_HAS_BIAS = (EPI_STORE, EPI_BIAS_GELU, EPI_BIAS_DROP_RES, EPI_STORE_F32, EPI_BIAS_GELU_DG, EPI_BIAS_DROP_RES_LN)
 EPI_HAS_RES = (EPI_BIAS_DROP_RES, EPI_ADD, EPI_DGELU, EPI_MUL, EPI_BIAS_DROP_RES_LN)
 EPI_DUAL = (EPI_BIAS_GELU, EPI_BIAS_GELU_DG, EPI_BIAS_DROP_RES_LN)

@@ -34,6 +34,11 @@ struct GemmArgs {
     const float* ln_gamma; const float* ln_beta;  // EPI_BIAS_DROP_RES_LN
     float* ln_mean; float* ln_rstd; float ln_eps;
     int ln_cl;                           // EPI_BIAS_DROP_RES_LN: CTAs per cluster = N / 128 column tiles of one row block
+    // EPI_CE_STATS / EPI_CE_GRAD (vocabulary GEMM fused with cross entropy)
+    const long long* ce_target;          // [M] target column of each row
+    float* ce_partial;                   // [M][ceil(N/128)][2]: (max, sum exp(x - max)) of each row over one column tile
+    float* ce_tlogit;                    // [M]: the logit at the target column
+    const float* ce_lse; const float* ce_scale;  // [M]: log-sum-exp of the row, upstream gradient of its loss
     long long* dbg;  // optional per-CTA phase timestamps (8 x int64 per CTA), bring-up only
     int dbg_mode;    // bring-up: 1 = skip the MMAs (TMA-only), 2 = skip the TMA loads (MMA-only)
 };
@@ -187,10 +192,11 @@ struct GemmCfg {
     static constexpr bool HAS_R = EPI == B200U_EPI_BIAS_DROP_RES || EPI == B200U_EPI_ADD || EPI == B200U_EPI_DGELU ||
                                   EPI == B200U_EPI_MUL || LN;
     static constexpr bool DUAL = EPI == B200U_EPI_BIAS_GELU || EPI == B200U_EPI_BIAS_GELU_DG;
-    static constexpr bool F32_OUT = EPI == B200U_EPI_ATOMIC_F32 || EPI == B200U_EPI_STORE_F32;
+    static constexpr bool CE_STATS = EPI == B200U_EPI_CE_STATS;
+    static constexpr bool F32_OUT = EPI == B200U_EPI_ATOMIC_F32 || EPI == B200U_EPI_STORE_F32 || CE_STATS;
     static constexpr bool HAS_BIAS = EPI == B200U_EPI_STORE || EPI == B200U_EPI_BIAS_GELU ||
                                      EPI == B200U_EPI_BIAS_DROP_RES || EPI == B200U_EPI_STORE_F32 ||
-                                     EPI == B200U_EPI_BIAS_GELU_DG || LN;
+                                     EPI == B200U_EPI_BIAS_GELU_DG || LN || CE_STATS || EPI == B200U_EPI_CE_GRAD;
     static constexpr int GROUP_COLS = F32_OUT ? 32 : 64;  // one 128-byte swizzled row per output group
     static constexpr int NUM_GROUPS = BLOCK_N / GROUP_COLS;
     static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
@@ -237,7 +243,7 @@ __device__ __forceinline__ void epi_math8(const uint32_t* acc, const float* bias
 #pragma unroll
     for (int i = 0; i < 4; ++i) v[i] = f2(__uint_as_float(acc[2 * i]), __uint_as_float(acc[2 * i + 1]));
     if (EPI == B200U_EPI_STORE || EPI == B200U_EPI_BIAS_GELU || EPI == B200U_EPI_BIAS_DROP_RES ||
-        EPI == B200U_EPI_BIAS_GELU_DG || EPI == B200U_EPI_BIAS_DROP_RES_LN) {
+        EPI == B200U_EPI_BIAS_GELU_DG || EPI == B200U_EPI_BIAS_DROP_RES_LN || EPI == B200U_EPI_CE_GRAD) {
         const float4 b0 = *reinterpret_cast<const float4*>(bias8);
         const float4 b1 = *reinterpret_cast<const float4*>(bias8 + 4);
         v[0] = f2_add(v[0], f2(b0.x, b0.y));
@@ -270,6 +276,20 @@ __device__ __forceinline__ void epi_math8(const uint32_t* acc, const float* bias
     } else if (EPI == B200U_EPI_MUL) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) out[i] = f2_to_bf16x2(f2_mul(v[i], f2_from_bf16x2(rr[i])));
+    } else if (EPI == B200U_EPI_CE_GRAD) {
+        // d loss / d logit = (softmax - onehot(target)) * upstream: the logits are recomputed, never stored
+        const bool ok = row < g.M;
+        const float lse = ok ? g.ce_lse[row] : 0.f, sc = ok ? g.ce_scale[row] : 0.f;
+        const long long tg = ok ? g.ce_target[row] : -1;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float x0, x1;
+            f2_get(v[i], x0, x1);
+            float p0 = __expf(x0 - lse), p1 = __expf(x1 - lse);
+            if ((long long)(col + 2 * i) == tg) p0 -= 1.0f;
+            if ((long long)(col + 2 * i + 1) == tg) p1 -= 1.0f;
+            out[i] = f2_to_bf16x2(f2(p0 * sc, p1 * sc));
+        }
     } else if (EPI == B200U_EPI_ADD) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) out[i] = f2_to_bf16x2(f2_add(v[i], f2_from_bf16x2(rr[i])));
@@ -631,8 +651,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             uint32_t ra[32], rb[32];
             if (have) tmem_ld_32x32(taddr + gi * Cfg::GROUP_COLS, ra);
             if (Cfg::F32_OUT) {
+                // cross-entropy statistics of this thread's row over this warp's column groups (online softmax)
+                float ce_m = -INFINITY, ce_s = 0.f, ce_t = 0.f;
+                bool ce_hit = false;
+                long long ce_tgt = -1;
+                if (Cfg::CE_STATS && row < g.M) ce_tgt = g.ce_target[row];
                 // fp32 output (wgrad reduce-add / fp32 store): 32-column groups, one 4 KB staging tile
                 auto stage_out = [&](const uint32_t (&r)[32], int col0) {
+                    if constexpr (Cfg::CE_STATS) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int c = n0 + col0 + j;
+                            const float x = __uint_as_float(r[j]) + bias_s[col0 + j];
+                            if (c < g.N) {
+                                if (x > ce_m) {
+                                    ce_s = ce_s * __expf(ce_m - x) + 1.0f;
+                                    ce_m = x;
+                                } else {
+                                    ce_s += __expf(x - ce_m);
+                                }
+                                if ((long long)c == ce_tgt) { ce_t = x; ce_hit = true; }
+                            }
+                        }
+                        return;
+                    }
                     if (lane == 0) bulk_wait_read_all();  // staging buffer free again?
                     __syncwarp();
 #pragma unroll
@@ -670,6 +712,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     stage_out(rb, gi * 32);
                     gi = gn;
                     have = more;
+                }
+                if constexpr (Cfg::CE_STATS) {
+                    // the two warps of a lane quadrant walked the even / odd column groups: merge them, then one
+                    // (max, sum) pair per (row, column tile) and the target logit leave for global memory
+                    float* xch = reinterpret_cast<float*>(stg);
+                    if (half == 1) {
+                        *reinterpret_cast<float4*>(xch + lane * 4) = make_float4(ce_m, ce_s, ce_t, ce_hit ? 1.f : 0.f);
+                    }
+                    asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+                    if (half == 0) {
+                        const float4 o = *reinterpret_cast<const float4*>(
+                            reinterpret_cast<const float*>(sStg + (ew + 4) * Cfg::STG_PER_WARP) + lane * 4);
+                        const float mm = fmaxf(ce_m, o.x);
+                        float ss = 0.f;
+                        if (ce_m > -INFINITY) ss += ce_s * __expf(ce_m - mm);
+                        if (o.x > -INFINITY) ss += o.y * __expf(o.x - mm);
+                        if (row < g.M) {
+                            reinterpret_cast<float2*>(g.ce_partial)[(size_t)row * g.n_tiles + n0 / BLOCK_N] = make_float2(mm, ss);
+                            if (ce_hit) g.ce_tlogit[row] = ce_t;
+                            else if (o.w != 0.f) g.ce_tlogit[row] = o.z;
+                        }
+                    }
                 }
             } else {
                 int prev = -1;  // side-input group whose TMA store may still be reading its slot
@@ -940,7 +1004,8 @@ static int launch_tc(const b200u_gemm_t* d, GemmArgs& g, cudaStream_t stream) {
     if (!B_MN) rc = make_tmap(&tmB, d->B, d->N, d->K, d->ldb, BLOCK_N / CLUSTER);
     else       rc = make_tmap(&tmB, d->B, d->K, d->N, d->ldb, BLOCK_K);
     if (rc) return rc;
-    rc = make_tmap(&tmC, d->C, d->M, d->N, d->ldc, 32, Cfg::F32_OUT);
+    if (Cfg::CE_STATS) tmC = tmA;   // no output matrix: the epilogue writes row statistics
+    else rc = make_tmap(&tmC, d->C, d->M, d->N, d->ldc, 32, Cfg::F32_OUT);
     if (rc) return rc;
     tmC2 = tmC;
     tmR = tmC;
@@ -1032,6 +1097,13 @@ static int dispatch_major(const b200u_gemm_t* d, GemmArgs& g, cudaStream_t strea
 
 template <int EPI>
 static int dispatch_bn(const b200u_gemm_t* d, GemmArgs& g, int block_n, cudaStream_t stream) {
+    if constexpr (EPI == B200U_EPI_CE_STATS || EPI == B200U_EPI_CE_GRAD) {
+        // hidden[M,K] . W[N,K]^T only, tcgen05 path only. Statistics are indexed by 128-column tiles.
+        B200U_CHECK_ARG(d->impl == 0 && !d->a_mn_major && !d->b_mn_major,
+                        "b200u_gemm: the cross-entropy epilogues need K-major A and B on the tcgen05 path");
+        if (EPI == B200U_EPI_CE_GRAD && block_n == 256) return launch_tc<256, false, false, EPI, 1>(d, g, stream);
+        return launch_tc<128, false, false, EPI, 1>(d, g, stream);
+    } else
     if (d->impl == 1) {
         dim3 grid((d->N + 31) / 32, (d->M + 127) / 128);
         g.splits = 1;
@@ -1082,9 +1154,48 @@ static int dispatch_bn(const b200u_gemm_t* d, GemmArgs& g, int block_n, cudaStre
     }
 }
 
+// one warp per row: merge the (max, sum) partials of the row's column tiles
+__global__ void __launch_bounds__(256)
+ce_finish_kernel(const float2* __restrict__ partial, const float* __restrict__ tlogit, float* __restrict__ lse,
+                 float* __restrict__ loss, int M, int n_tiles) {
+    pdl_sync();
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= M) return;
+    float m = -INFINITY, s_ = 0.f;
+    for (int t = lane; t < n_tiles; t += 32) {
+        const float2 p = partial[(size_t)row * n_tiles + t];
+        const float mm = fmaxf(m, p.x);
+        s_ = (m > -INFINITY ? s_ * __expf(m - mm) : 0.f) + (p.x > -INFINITY ? p.y * __expf(p.x - mm) : 0.f);
+        m = mm;
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        const float m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, s_, o);
+        const float mm = fmaxf(m, m2);
+        s_ = (m > -INFINITY ? s_ * __expf(m - mm) : 0.f) + (m2 > -INFINITY ? s2 * __expf(m2 - mm) : 0.f);
+        m = mm;
+    }
+    if (lane == 0) {
+        const float l = m + logf(s_);
+        lse[row] = l;
+        if (loss) loss[row] = l - tlogit[row];
+    }
+}
+
 }  // namespace b200u
 
 using namespace b200u;
+
+extern "C" int b200u_ce_finish(const float* partial, const float* tlogit, float* lse, float* loss, int M, int n_tiles,
+                               b200u_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    B200U_CHECK_ARG(partial && tlogit && lse && n_tiles > 0 && ((uintptr_t)partial & 7) == 0, "ce_finish: bad arguments");
+    if (M == 0) return B200U_OK;
+    launch_k(ce_finish_kernel, dim3((M + 7) / 8), dim3(256), 0, stream, (const float2*)partial, tlogit, lse, loss, M, n_tiles);
+    B200U_CHECK_LAUNCH("ce_finish");
+    return B200U_OK;
+}
 
 // Bring-up aid: when set, every tcgen05 GEMM CTA writes 8 clock64() phase stamps to ptr[cta*8..].
 extern "C" int b200u_gemm_debug_stamps(long long* device_ptr) {
@@ -1101,7 +1212,14 @@ extern "C" int b200u_gemm(const b200u_gemm_t* d, b200u_stream_t stream_) {
     B200U_CHECK_ARG(d != nullptr, "b200u_gemm: null descriptor");
     B200U_CHECK_ARG(d->M > 0 && d->N > 0 && d->K > 0, "b200u_gemm: bad shape M=%d N=%d K=%d", d->M,
                     d->N, d->K);
-    B200U_CHECK_ARG(d->A && d->B && d->C, "b200u_gemm: null operand pointer");
+    const bool ce_stats = d->epilogue == B200U_EPI_CE_STATS, ce_grad = d->epilogue == B200U_EPI_CE_GRAD;
+    B200U_CHECK_ARG(d->A && d->B && (d->C || ce_stats), "b200u_gemm: null operand pointer");
+    if (ce_stats)
+        B200U_CHECK_ARG(d->ce_target && d->ce_partial && d->ce_tlogit && d->bias && ((uintptr_t)d->ce_partial & 7) == 0,
+                        "b200u_gemm: EPI_CE_STATS needs bias, ce_target, ce_partial and ce_tlogit");
+    if (ce_grad)
+        B200U_CHECK_ARG(d->ce_target && d->ce_lse && d->ce_scale && d->bias,
+                        "b200u_gemm: EPI_CE_GRAD needs bias, ce_target, ce_lse and ce_scale");
     B200U_CHECK_ARG(d->epilogue >= 0 && d->epilogue < B200U_EPI_COUNT, "b200u_gemm: bad epilogue %d",
                     d->epilogue);
     B200U_CHECK_ARG(d->lda % 8 == 0 && d->ldb % 8 == 0,
@@ -1139,6 +1257,8 @@ extern "C" int b200u_gemm(const b200u_gemm_t* d, b200u_stream_t stream_) {
     g.ln_gamma = d->ln_gamma; g.ln_beta = d->ln_beta; g.ln_mean = d->ln_mean; g.ln_rstd = d->ln_rstd;
     g.ln_eps = d->ln_eps;
     g.ln_cl = 1;  // set by dispatch (N / tile width)
+    g.ce_target = d->ce_target; g.ce_partial = d->ce_partial; g.ce_tlogit = d->ce_tlogit;
+    g.ce_lse = d->ce_lse; g.ce_scale = d->ce_scale;
     const float p = (d->epilogue == B200U_EPI_BIAS_DROP_RES || ln) ? d->drop.p : 0.f;
     B200U_CHECK_ARG(p >= 0.f && p < 1.f, "b200u_gemm: dropout p out of range");
     g.drop.thresh16 = (uint32_t)(p * 65536.0f + 0.5f);
@@ -1164,6 +1284,7 @@ extern "C" int b200u_gemm(const b200u_gemm_t* d, b200u_stream_t stream_) {
         if (reduce) block_n = d->N >= 256 ? 256 : 128;
         else block_n = (d->N >= 256 && c256 <= c128) ? 256 : 128;
     }
+    if (ce_stats) block_n = 128;
     // (epilogues with a side-input tile keep it in smem and write their output over it in place:
     //  3 pipeline stages remain at 256-wide tiles, 5 at 128)
     int splits = d->splits;
@@ -1192,6 +1313,8 @@ extern "C" int b200u_gemm(const b200u_gemm_t* d, b200u_stream_t stream_) {
         case B200U_EPI_BIAS_GELU_DG:  return dispatch_bn<B200U_EPI_BIAS_GELU_DG>(d, g, block_n, stream);
         case B200U_EPI_MUL:           return dispatch_bn<B200U_EPI_MUL>(d, g, block_n, stream);
         case B200U_EPI_BIAS_DROP_RES_LN: return dispatch_bn<B200U_EPI_BIAS_DROP_RES_LN>(d, g, d->block_n, stream);
+        case B200U_EPI_CE_STATS:      return dispatch_bn<B200U_EPI_CE_STATS>(d, g, block_n, stream);
+        case B200U_EPI_CE_GRAD:       return dispatch_bn<B200U_EPI_CE_GRAD>(d, g, block_n, stream);
     }
     return B200U_ERR_ARG;
 }

@@ -607,3 +607,63 @@ class LinearFn(torch.autograd.Function):
 
 def linear(x, weight, bias=None, transposed=False, gelu=False, out_f32=False):
     return LinearFn.apply(x, weight, bias, transposed, gelu, out_f32)
+
+
+class VocabCrossEntropyFn(torch.autograd.Function):
+    """F.cross_entropy(x·Wᵀ + b, targets, reduction='none') WITHOUT the [n, vocab] logits (the MLM decoder tied to
+    the word embeddings followed by the loss, model/layer.py:204-221 + model/pretrain.py:97-98).
+
+    forward: one GEMM whose epilogue reduces every 128-column tile of a row to (max, sum exp) and picks out the
+    target logit (EPI_CE_STATS), then b200u_ce_finish -> lse, loss. backward: the GEMM is run again with the
+    epilogue that turns the recomputed logits into d logits = (softmax - onehot) * d loss as the bf16 operand
+    (EPI_CE_GRAD) of the decoder's dgrad / wgrad GEMMs and the bias column sums. fp32 logits are never stored."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, targets):
+        assert x.dim() == 2
+        x = x.to(torch.bfloat16).contiguous()
+        n, K = x.shape
+        N = weight.shape[0]
+        if n == 0:
+            ctx.empty = True
+            ctx.shape = (n, K)
+            return torch.zeros(0, device=x.device, dtype=torch.float32)
+        ctx.empty = False
+        w16 = shadow_for(weight)
+        targets = _ids64(targets, "targets")
+        if bias is None:
+            bias = torch.zeros(N, device=x.device, dtype=torch.float32)
+            ctx.has_bias = False
+        else:
+            ctx.has_bias = True
+        nt = (N + 127) // 128
+        partial = torch.empty(n, nt, 2, device=x.device, dtype=torch.float32)
+        tlogit = torch.zeros(n, device=x.device, dtype=torch.float32)
+        ops.gemm(x, w16, epilogue=_lib.EPI_CE_STATS, bias=bias, ce=dict(target=targets, partial=partial, tlogit=tlogit))
+        lse, loss = ops.ce_finish(partial, tlogit)
+        ctx.save_for_backward(x, targets, lse)
+        ctx.params = (weight, bias, w16)
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        if ctx.empty:
+            return torch.zeros(ctx.shape, device=dloss.device, dtype=torch.bfloat16), None, None, None
+        x, targets, lse = ctx.saved_tensors
+        weight, bias, w16 = ctx.params
+        n, K = x.shape
+        N = weight.shape[0]
+        ld = _pad8(N)
+        dyb = torch.zeros(n, ld, device=x.device, dtype=torch.bfloat16)   # 16-byte aligned rows, zero pad columns
+        dyv = dyb[:, :N]
+        ops.gemm(x, w16, epilogue=_lib.EPI_CE_GRAD, out=dyv, bias=bias,
+                 ce=dict(target=targets, lse=lse, scale=dloss.float().contiguous()))
+        if ctx.has_bias:
+            ops.colsum_accum(dyb, grad_buf(bias)) if ld == N else grad_buf(bias).add_(dyv.float().sum(0))
+        ops.gemm(dyv, x, a_mn=True, b_mn=True, epilogue=EPI_ATOMIC_F32, out=grad_buf(weight))
+        dx = ops.gemm(dyv, w16, b_mn=True)
+        return dx, None, None, None
+
+
+def vocab_cross_entropy(x, weight, bias, targets):
+    return VocabCrossEntropyFn.apply(x, weight, bias, targets)

@@ -146,6 +146,12 @@ class BertLMPredictionHead(nn.Module):
         hidden_states = self.transform(hidden_states)
         return F_.linear(hidden_states, self.decoder.weight, self.bias, out_f32=True)
 
+    def cross_entropy(self, hidden_states, targets):
+        """F.cross_entropy(self(hidden_states), targets, reduction='none') with the decoder GEMM and the loss fused:
+        the [n, vocab] logits are never written (functional.VocabCrossEntropyFn)."""
+        hidden_states = self.transform(hidden_states)
+        return F_.vocab_cross_entropy(hidden_states, self.decoder.weight, self.bias, targets)
+
 
 class BertOnlyMLMHead(nn.Module):
     """model/layer.py:224-233."""
@@ -156,3 +162,6 @@ class BertOnlyMLMHead(nn.Module):
 
     def forward(self, sequence_output):
         return self.predictions(sequence_output)
+
+    def cross_entropy(self, sequence_output, targets):
+        return self.predictions.cross_entropy(sequence_output, targets)

@@ -3,8 +3,9 @@
 Same classes, state_dict keys (uniter.*, cls.predictions.*, feat_regress.*, region_classifier.*,
 itm_output.*; tied decoder / feat_regress weights) and `forward(batch, task, compute_loss)` task
 dispatch. Encoder, head GEMMs, LayerNorms, pooler and the IPOT alignment run on b200u kernels; the
-per-task loss reductions (cross entropy / MSE / KL over the few hundred masked rows) stay torch
-functional calls on the fp32 head outputs (SURVEY.md §8f row 3 lists fusing them as "next").
+MLM loss is the fused vocabulary GEMM + online log-softmax + NLL (functional.VocabCrossEntropyFn: the
+[n_masked, 28996] logits are never written); the other per-task loss reductions (MSE / KL / 2-way cross
+entropy over a few hundred rows) stay torch functional calls on the fp32 head outputs.
 """
 from collections import defaultdict
 
@@ -60,6 +61,8 @@ class UniterForPretraining(UniterPreTrainedModel):
                                                     self.uniter.img_embeddings.img_linear.weight)
         self.region_classifier = RegionClassification(config.hidden_size, img_label_dim)
         self.itm_output = nn.Linear(config.hidden_size, 2)
+        # MLM loss through the fused vocabulary GEMM + cross entropy (False: materialise fp32 logits like the reference)
+        self.fused_vocab_ce = True
         self.apply(self.init_weights)
 
     def forward(self, batch, task, compute_loss=True):
@@ -93,10 +96,12 @@ class UniterForPretraining(UniterPreTrainedModel):
                                       gather_index, output_all_encoded_layers=False)
         sequence_output = sequence_output[:, :input_ids.size(1), :]       # text part only
         masked_output = self._compute_masked_hidden(sequence_output, txt_labels != -1)
-        prediction_scores = self.cls(masked_output)
         if compute_loss:
-            return F.cross_entropy(prediction_scores, txt_labels[txt_labels != -1], reduction='none')
-        return prediction_scores
+            if self.fused_vocab_ce:
+                # decoder GEMM + log-softmax + NLL in one pass over the vocabulary: no [n_masked, 28996] logits
+                return self.cls.cross_entropy(masked_output, txt_labels[txt_labels != -1])
+            return F.cross_entropy(self.cls(masked_output), txt_labels[txt_labels != -1], reduction='none')
+        return self.cls(masked_output)
 
     def _compute_masked_hidden(self, hidden, mask):
         """ get only the masked region (don't compute unnecessary hiddens) """

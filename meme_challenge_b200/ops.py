@@ -18,23 +18,26 @@ def _ld(t):
 
 
 def gemm(a, b, *, a_mn=False, b_mn=False, epilogue=EPI_STORE, out=None, out2=None, bias=None,
-         res=None, drop=None, splits=0, block_n=0, impl=0, cluster=0, colsum=None, ln=None):
+         res=None, drop=None, splits=0, block_n=0, impl=0, cluster=0, colsum=None, ln=None, ce=None):
     """acc[M,N] = sum_k A(m,k) B(n,k) with a fused epilogue (see include/b200u.h, K3).
 
     a: [M,K] (or [K,M] when a_mn), b: [N,K] (or [K,N] when b_mn); bf16, row-major.
     colsum (EPI_MUL): f32 [N], += column sums of the output. ln (EPI_BIAS_DROP_RES_LN): tuple
     (gamma f32 [N], beta f32 [N], eps, mean f32 [M] or None, rstd f32 [M] or None); out = pre-LayerNorm
     values, out2 = LayerNorm output. Dual-output epilogues return (out, out2).
+    ce (EPI_CE_STATS / EPI_CE_GRAD): dict with `target` (i64 [M]) and, for STATS, `partial` (f32 [M, ceil(N/128), 2])
+    and `tlogit` (f32 [M]) -- no output matrix, returns None --, for GRAD `lse` and `scale` (f32 [M]).
     """
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
     M, K = (a.shape[1], a.shape[0]) if a_mn else (a.shape[0], a.shape[1])
     N, Kb = (b.shape[1], b.shape[0]) if b_mn else (b.shape[0], b.shape[1])
     assert K == Kb, "inner dimensions differ: %d vs %d" % (K, Kb)
     f32_out = epilogue in (EPI_ATOMIC_F32, EPI_STORE_F32)
-    if out is None:
+    stats_only = epilogue == _lib.EPI_CE_STATS
+    if out is None and not stats_only:
         assert epilogue != EPI_ATOMIC_F32, "EPI_ATOMIC_F32 accumulates into an existing buffer"
         out = torch.empty(M, N, device=a.device, dtype=torch.float32 if f32_out else torch.bfloat16)
-    assert out.dtype == (torch.float32 if f32_out else torch.bfloat16) and tuple(out.shape) == (M, N)
+    assert stats_only or (out.dtype == (torch.float32 if f32_out else torch.bfloat16) and tuple(out.shape) == (M, N))
     if epilogue in EPI_DUAL and out2 is None:
         out2 = torch.empty(M, N, device=a.device, dtype=torch.bfloat16)
     g = _lib.GemmT()
@@ -42,7 +45,18 @@ def gemm(a, b, *, a_mn=False, b_mn=False, epilogue=EPI_STORE, out=None, out2=Non
     g.A, g.lda, g.a_mn_major = a.data_ptr(), _ld(a), int(a_mn)
     g.B, g.ldb, g.b_mn_major = b.data_ptr(), _ld(b), int(b_mn)
     g.epilogue = epilogue
-    g.C, g.ldc = out.data_ptr(), _ld(out)
+    if not stats_only:
+        g.C, g.ldc = out.data_ptr(), _ld(out)
+    if ce is not None:
+        tgt = ce["target"]
+        assert tgt.dtype == torch.int64 and tgt.numel() == M and tgt.is_contiguous()
+        g.ce_target = tgt.data_ptr()
+        for k in ("partial", "tlogit", "lse", "scale"):
+            t = ce.get(k)
+            if t is not None:
+                assert t.dtype == torch.float32 and t.is_contiguous()
+                assert t.numel() == (M * ((N + 127) // 128) * 2 if k == "partial" else M)
+                setattr(g, "ce_" + k, t.data_ptr())
     if out2 is not None:
         g.C2, g.ldc2 = out2.data_ptr(), _ld(out2)
     if bias is not None:
@@ -67,6 +81,15 @@ def gemm(a, b, *, a_mn=False, b_mn=False, epilogue=EPI_STORE, out=None, out2=Non
         g.ln_rstd = rstd.data_ptr() if rstd is not None else None
     _lib.check(_lib.lib().b200u_gemm(C.byref(g), _lib.stream_ptr()), "b200u_gemm")
     return (out, out2) if epilogue in EPI_DUAL else out
+
+
+def ce_finish(partial, tlogit):
+    """(lse [M], loss [M]) from the EPI_CE_STATS partials."""
+    M, nt = partial.shape[0], partial.shape[1]
+    lse = torch.empty(M, device=partial.device, dtype=torch.float32)
+    loss = torch.empty(M, device=partial.device, dtype=torch.float32)
+    _call("b200u_ce_finish", P(partial), P(tlogit), P(lse), P(loss), M, nt)
+    return lse, loss
 
 
 # --------------------------------------------------------------------------------------------

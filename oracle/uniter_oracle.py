@@ -161,7 +161,7 @@ def meme_uniter_forward(sd, cfg, **kw):
 def bce_loss(logits, labels, pos_wt):
     """train_template.py:64-65,98-99: BCEWithLogitsLoss(pos_weight=[pos_wt]) on preds.squeeze(1)."""
     return F.binary_cross_entropy_with_logits(logits.squeeze(1), labels.float(),
-                                              pos_weight=torch.tensor([pos_wt]))
+                                              pos_weight=torch.tensor([pos_wt], device=logits.device))
 
 
 # ----------------------------------------------------------------------------------------------

@@ -448,16 +448,29 @@ def test_tiny_model_against_reference_golden(golden_dir):
         assert d[valid].max() < 5e-2
 
 
-def _oracle_run(m, cfg_dict, b, pos_wt=1.8, want_grads=True):
-    sd = {k: v.detach().float().cpu().clone().requires_grad_(want_grads) for k, v in m.state_dict().items()}
+def _oracle_run(m, cfg_dict, b, pos_wt=1.8, want_grads=True, device="cpu"):
+    """The fp32 oracle on the model's weights. device="cuda": the same restatement evaluated by torch's fp32 CUDA
+    kernels (TF32 off) so full-depth large configurations stay in seconds; results come back on the CPU."""
+    sd = {k: v.detach().float().to(device).clone().requires_grad_(want_grads) for k, v in m.state_dict().items()}
     kw = dict(input_ids=b["input_ids"], position_ids=b["position_ids"], img_feat=b["img_feat"],
               img_pos_feat=b["img_pos_feat"], attention_mask=b["attn_mask"], gather_index=b["gather_index"])
-    with torch.set_grad_enabled(want_grads):
-        logits = O.meme_uniter_forward(sd, cfg_dict, **kw)
-        loss = O.bce_loss(logits, b["labels"], pos_wt)
-    if want_grads:
-        loss.backward()
-    return logits.detach(), loss.detach(), sd
+    kw = {k: v.to(device) for k, v in kw.items()}
+    tf32 = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        with torch.set_grad_enabled(want_grads):
+            logits = O.meme_uniter_forward(sd, cfg_dict, **kw)
+            loss = O.bce_loss(logits, b["labels"].to(device), pos_wt)
+        if want_grads:
+            loss.backward()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+    if device != "cpu":
+        class _G(object):
+            def __init__(self, g):
+                self.grad = g
+        sd = {k: _G(None if v.grad is None else v.grad.cpu()) for k, v in sd.items()}
+    return logits.detach().cpu(), loss.detach().cpu(), sd
 
 
 BASE = dict(vocab_size=28996, hidden_size=768, num_hidden_layers=12, num_attention_heads=12,
@@ -597,6 +610,46 @@ def test_large_c4_shapes_fwd_bwd_against_oracle():
               "uniter_model.encoder.layer.0.output.LayerNorm.weight",
               "uniter_model.img_embeddings.img_linear.weight"):
         assert _cos(dict(m.named_parameters())[n].grad.detach().cpu(), sd[n].grad) > 0.98, n
+
+
+LARGE = dict(vocab_size=28996, hidden_size=1024, num_hidden_layers=24, num_attention_heads=16,
+             intermediate_size=4096, hidden_act="gelu", hidden_dropout_prob=0.1,
+             attention_probs_dropout_prob=0.1, max_position_embeddings=512, type_vocab_size=2,
+             initializer_range=0.02)
+
+
+def test_large_c4_full_depth_fwd_bwd_against_oracle():
+    """BASELINE config 4 at FULL depth (config/uniter-large.json: 24 layers, H=1024, I=4096, 16 heads) on the C2
+    batch shape (16 memes, 64 tokens, 36-100 regions): fwd + bwd against the fp32 oracle evaluated on the GPU.
+    Logit / loss tolerances as C2; per-tensor gradient rel-L2 bounds for twice the depth."""
+    _require_gpu()
+    b = O.synth_batch(16, 64, 100, seed=4321, variable=True)
+    m = _build(LARGE, 2048).eval()
+    logits = m(**_kw(b))
+    loss = torch.nn.BCEWithLogitsLoss(pos_weight=torch.tensor([1.8], device=DEV))(
+        logits.squeeze(1), b["labels"].float().to(DEV))
+    loss.backward()
+    ref_logits, ref_loss, sd = _oracle_run(m, LARGE, b, device=DEV)
+    assert (logits.detach().cpu() - ref_logits).abs().max() <= LOGIT_TOL
+    assert abs(loss.item() - ref_loss.item()) <= LOSS_RTOL * abs(ref_loss.item())
+    worst = []
+    for n, p in m.named_parameters():
+        want = sd[n].grad
+        if want is None or p.grad is None or want.abs().max() < 1e-8:
+            continue
+        got_g = p.grad.detach().cpu().float()
+        worst.append((((got_g - want).norm() / want.norm()).item(), n))
+    worst.sort(reverse=True)
+    if os.environ.get("B200U_PRINT_REL"):
+        print("large: per-tensor rel-L2 (worst 8):", [(round(r, 4), n) for r, n in worst[:8]], "median", worst[len(worst) // 2][0])
+    # measured: worst 0.116 (query / key weights of the last layers, whose gradients pass through 24 softmaxes'
+    # worth of bf16 rounding), median 0.03
+    assert len(worst) > 370 and worst[0][0] <= 0.15 and worst[len(worst) // 2][0] <= 0.06, (worst[:5], worst[len(worst) // 2])
+    names = [n for n, p in m.named_parameters() if sd[n].grad is not None and p.grad is not None]
+    got = torch.cat([dict(m.named_parameters())[n].grad.detach().cpu().flatten() for n in names])
+    want = torch.cat([sd[n].grad.flatten() for n in names])
+    assert _cos(got, want) > 0.995
+    assert abs(got.norm().item() / want.norm().item() - 1) < 2e-2
 
 
 def test_train_step_matches_reference_optimizer_semantics():
@@ -953,16 +1006,52 @@ def _pretrain_setup(golden_dir):
     return g, sd, b, m.to(DEV).eval()
 
 
+MEAN_LOSS_RTOL = 1e-3
+
+
+def test_vocab_cross_entropy_fused_against_torch():
+    """EPI_CE_STATS / EPI_CE_GRAD (model/layer.py:204-221 decoder + model/pretrain.py:97-98 F.cross_entropy): the
+    fused path never materialises the [n, 28996] logits. Against fp32 torch on the same bf16-rounded operands:
+    per-row loss, d hidden, d weight (tied word embeddings), d bias."""
+    _require_gpu()
+    from meme_challenge_b200 import functional as F_
+    torch.manual_seed(3)
+    for n, V, K in ((150, 28996, 768), (7, 1000, 64), (300, 515, 128)):
+        x = (torch.randn(n, K, device=DEV) * 0.7).bfloat16().requires_grad_(True)
+        W = torch.nn.Parameter((torch.randn(V, K, device=DEV) * 0.05).bfloat16().float())
+        bias = torch.nn.Parameter(torch.randn(V, device=DEV) * 0.1)
+        tgt = torch.randint(0, V, (n,), device=DEV)
+        tgt[0] = V - 1            # last (ragged) column tile
+        wts = torch.rand(n, device=DEV) + 0.5
+        loss = F_.vocab_cross_entropy(x, W, bias, tgt)
+        (loss * wts).sum().backward()
+        xr = x.detach().float().requires_grad_(True)
+        Wr = W.detach().clone().requires_grad_(True)
+        br = bias.detach().clone().requires_grad_(True)
+        ref = torch.nn.functional.cross_entropy(xr @ Wr.t() + br, tgt, reduction="none")
+        (ref * wts).sum().backward()
+        assert torch.allclose(loss, ref, rtol=1e-4, atol=2e-4), (n, V, (loss - ref).abs().max().item())
+        for got, want, name in ((x.grad.float(), xr.grad, "dx"), (W.grad, Wr.grad, "dW"), (bias.grad, br.grad, "db")):
+            rel = ((got - want).norm() / want.norm()).item()
+            assert rel < 1e-2, (n, V, name, rel)
+
+
 def test_pretraining_tasks_against_reference_golden(golden_dir):
     _require_gpu()
     g, sd, b, m = _pretrain_setup(golden_dir)
     with torch.no_grad():
-        for task, rtol in (("mlm", 2e-2), ("mrfr", 5e-2), ("itm", 2e-2), ("mrc-kl", 5e-2), ("mrc", 2e-2)):
+        # per-sample losses, relative to the largest one (measured 5e-4 / 2e-3 / 3e-4 / 6e-4 / 7e-4)
+        for task, rtol in (("mlm", 3e-3), ("mrfr", 1e-2), ("itm", 2e-3), ("mrc-kl", 4e-3), ("mrc", 4e-3)):
             got = m(b, task).float().cpu().numpy()
             want = g["loss." + task]
             assert got.shape == want.shape, task
             err = np.abs(got - want).max() / (np.abs(want).max() + 1e-6)
             assert err < rtol, (task, err)
+            # the quantity training optimises: the mean task loss, within MEAN_LOSS_RTOL of the reference's
+            mean_err = abs(float(got.mean()) - float(want.mean())) / (abs(float(want.mean())) + 1e-12)
+            if os.environ.get("B200U_PRINT_REL"):
+                print("pretrain %s: max rel err %.2e, mean-loss rel err %.2e" % (task, err, mean_err))
+            assert mean_err < MEAN_LOSS_RTOL, (task, mean_err)
         scores = m(b, "mlm", compute_loss=False).float().cpu().numpy()
         assert np.abs(scores - g["scores.mlm"]).max() < 2e-2
     # ITM computes the OT distance like the reference does (and drops it); check it against the oracle
