@@ -32,7 +32,7 @@ if want("gemm"):
         a = torch.randn((K, M) if am else (M, K), device=dev).bfloat16()
         b = torch.randn((K, N) if bm else (N, K), device=dev).bfloat16()
         for ep in range(E.EPI_COUNT):
-            if ep == E.EPI_BIAS_DROP_RES_LN:
+            if ep in (E.EPI_BIAS_DROP_RES_LN, E.EPI_CE_STATS, E.EPI_CE_GRAD):
                 continue
             for bn in (128, 256):
                 f32 = ep in (E.EPI_ATOMIC_F32, E.EPI_STORE_F32)
@@ -57,6 +57,17 @@ if want("gemm"):
                  res=torch.randn(M, N, device=dev).bfloat16(), drop=_lib.dropout_t(seed, 3, 0.1),
                  ln=(torch.ones(N, device=dev), torch.zeros(N, device=dev), 1e-12,
                      torch.empty(M, device=dev), torch.empty(M, device=dev)))
+    # vocabulary GEMM + cross entropy epilogues (ragged last column tile), forward and backward
+    from meme_challenge_b200 import functional as F_
+    xh = torch.randn(45, 64, device=dev).bfloat16().requires_grad_(True)
+    Wv = torch.nn.Parameter(torch.randn(515, 64, device=dev) * 0.05)
+    bv = torch.nn.Parameter(torch.zeros(515, device=dev))
+    F_.vocab_cross_entropy(xh, Wv, bv, torch.randint(0, 515, (45,), device=dev)).sum().backward()
+    # reduce step of the copy-engine gradient exchange
+    import ctypes as C
+    own = torch.randn(4096, device=dev).bfloat16()
+    peers = [torch.randn(4096, device=dev).bfloat16() for _ in range(7)]
+    ops._call("b200u_slice_sum_bf16", ops.P(own), (C.c_void_p * 7)(*[t.data_ptr() for t in peers]), 7, C.c_size_t(4096))
     torch.cuda.synchronize()
     print("gemm ok", flush=True)
 
