@@ -323,7 +323,7 @@ __global__ void __launch_bounds__(256)
 embedding_segment_add_kernel(const bf16* __restrict__ d, const long long* __restrict__ ids_sorted,
                              const long long* __restrict__ perm, float* __restrict__ table_grad, int n,
                              int H, long long padding_idx, int nchunk, long long rows,
-                             unsigned* __restrict__ err) {
+                             unsigned* __restrict__ err, double* __restrict__ sumsq) {
     pdl_sync();
     const int lane = threadIdx.x & 31;
     const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -371,12 +371,18 @@ embedding_segment_add_kernel(const bf16* __restrict__ d, const long long* __rest
         if (cnt < 8) break;
         q += 8;
     }
+    float sq = 0.f;
     if (active) {
         float4* o = reinterpret_cast<float4*>(table_grad + (size_t)id * H + col);
         float4 a = o[0], b = o[1];
         a.x += acc[0]; a.y += acc[1]; a.z += acc[2]; a.w += acc[3];
         b.x += acc[4]; b.y += acc[5]; b.z += acc[6]; b.w += acc[7];
         o[0] = a; o[1] = b;
+        sq = (a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w) + (b.x * b.x + b.y * b.y + b.z * b.z + b.w * b.w);
+    }
+    if (sumsq) {   // the table's share of the global gradient norm, valid when the table was zero before this launch
+        sq = warp_sum(sq);
+        if (lane == 0) atomicAdd(sumsq, (double)sq);
     }
 }
 
@@ -511,7 +517,7 @@ extern "C" int b200u_embedding_scatter_add(const void* d, const long long* ids, 
 
 extern "C" int b200u_embedding_segment_add(const void* d, const long long* ids_sorted, const long long* perm,
                                            float* table_grad, int n, int H, long long padding_idx,
-                                           long long rows, b200u_stream_t stream_) {
+                                           long long rows, double* sumsq, b200u_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     B200U_CHECK_ARG(d && ids_sorted && perm && table_grad, "embedding_segment_add: null pointer");
     B200U_CHECK_ARG(H % 8 == 0, "embedding_segment_add: H must be a multiple of 8");
@@ -519,7 +525,7 @@ extern "C" int b200u_embedding_segment_add(const void* d, const long long* ids_s
     const int nchunk = (H + 255) / 256;
     const long long warps = (long long)n * nchunk;
     launch_k(embedding_segment_add_kernel, dim3((unsigned)((warps + 7) / 8)), dim3(256), 0, stream, (const bf16*)d,
-             ids_sorted, perm, table_grad, n, H, padding_idx, nchunk, rows, dev_err_ptr());
+             ids_sorted, perm, table_grad, n, H, padding_idx, nchunk, rows, dev_err_ptr(), sumsq);
     B200U_CHECK_LAUNCH("embedding_segment_add_kernel");
     return B200U_OK;
 }

@@ -46,7 +46,8 @@ class GradBuckets(object):
     folded into the optimizer's gradient scale. Works on any backend (NCCL on GPUs, gloo in the
     CPU tests)."""
 
-    def __init__(self, entries, flat_grad, process_group=None, world=1, comm_dtype=None, comm_impl="auto"):
+    def __init__(self, entries, flat_grad, process_group=None, world=1, comm_dtype=None, comm_impl="auto",
+                 tail_lo=None):
         self.grad = flat_grad
         self.pg = process_group
         self.world = world
@@ -77,20 +78,33 @@ class GradBuckets(object):
             want_ce = comm_impl in ("auto", "ce") and flat_grad.is_cuda and \
                 os.environ.get("B200U_DP_IMPL", "ce") != "nccl"
             if want_ce:
+                # tail_lo (end of the word-embedding table, whose rows travel sparsely): the dense rest of the
+                # embedding bucket [tail_lo, first layer) joins the bf16 symmetric range as one more bucket
+                tail = tail_lo if (tail_lo is not None and self.segments[0][0] <= tail_lo < self.segments[0][1]
+                                   and tail_lo % 8 == 0) else None
+                err = None
                 try:
-                    self._setup_peer(n - self.g16_lo)
+                    self._setup_peer(n, tail)
                 except Exception as e:   # no P2P / symmetric memory on this box: NCCL path
+                    err = e
+                # every rank must take the same path: agree on the outcome
+                ok = torch.tensor([0 if err is not None else 1], device=flat_grad.device, dtype=torch.int32)
+                torch.distributed.all_reduce(ok, op=torch.distributed.ReduceOp.MIN, group=process_group)
+                if int(ok.item()) == 0:
                     if comm_impl == "ce":
-                        raise
+                        raise err if err is not None else RuntimeError("symmetric memory unavailable on a peer rank")
                     if torch.distributed.get_rank(process_group) == 0:
-                        print("b200u: symmetric-memory gradient exchange unavailable (%s); using NCCL all-reduce"
-                              % (str(e).splitlines()[0] if str(e) else type(e).__name__), file=sys.stderr)
+                        msg = (str(err).splitlines()[0] if err is not None and str(err) else type(err).__name__)
+                        print("b200u: symmetric-memory gradient exchange unavailable (%s); using NCCL all-reduce" % msg,
+                              file=sys.stderr)
                     self.peer = None
+                    self.g16 = None
+                    self.g16_lo = self.segments[1][0]
             if self.peer is None:
                 self.g16 = torch.zeros(n - self.g16_lo, device=flat_grad.device, dtype=torch.bfloat16)
 
     # ------------------------------------------------------------------ copy-engine all-reduce over NVLink
-    def _setup_peer(self, n16):
+    def _setup_peer(self, n_total, tail_lo=None):
         """Two-shot all-reduce of the bf16 layer buckets WITHOUT collective kernels on the SMs.
 
         An NCCL ring all-reduce keeps 8-32 CTAs resident for ~80 us per layer bucket while the backward's
@@ -111,12 +125,16 @@ class GradBuckets(object):
         rank = dist.get_rank(self.pg)
         assert W - 1 <= 15, "b200u_slice_sum_bf16 takes at most 15 peers"
         group = self.pg if self.pg is not None else dist.group.WORLD
-        # per bucket: slice length (multiple of 8 elements = 16 bytes) and staging offset
+        g16_lo = self.segments[1][0] if tail_lo is None else tail_lo
+        n16 = n_total - g16_lo
+        # per bucket: slice length (multiple of 8 elements = 16 bytes) and staging offset; the optional last plan
+        # entry is the dense tail of the embedding bucket
+        ranges = list(self.segments[1:]) + ([(tail_lo, self.segments[0][1])] if tail_lo is not None else [])
         plan, stage_off = [], 0
-        for (lo, hi) in self.segments[1:]:
+        for (lo, hi) in ranges:
             ln = hi - lo
             sl = ((ln + W - 1) // W + 7) // 8 * 8
-            plan.append((lo - self.g16_lo, ln, sl, stage_off))
+            plan.append((lo - g16_lo, ln, sl, stage_off))
             stage_off += W * sl
         g16 = symm_mem.empty(n16, dtype=torch.bfloat16, device=dev)
         stage = symm_mem.empty(max(stage_off, 8), dtype=torch.bfloat16, device=dev)
@@ -125,16 +143,23 @@ class GradBuckets(object):
         h_s = symm_mem.rendezvous(stage, group)
         peers_g = [g16 if p == rank else h_g.get_buffer(p, (n16,), torch.bfloat16) for p in range(W)]
         peers_s = [stage if p == rank else h_s.get_buffer(p, (stage.numel(),), torch.bfloat16) for p in range(W)]
+        # word-embedding rows of the window (sparse exchange): one slot per rank, filled by peer copies
+        ROWS_MAX = 8192 * 1024      # elements per rank slot (8192 rows of H = 1024)
+        rows = symm_mem.empty(W * ROWS_MAX, dtype=torch.bfloat16, device=dev)
+        h_r = symm_mem.rendezvous(rows, group)
+        peers_r = [rows if p == rank else h_r.get_buffer(p, (rows.numel(),), torch.bfloat16) for p in range(W)]
         self.g16 = g16
-        self.peer = dict(rank=rank, plan=plan, stage=stage, h=h_g, h_s=h_s, peers_g=peers_g, peers_s=peers_s)
+        self.g16_lo = g16_lo
+        self.peer = dict(rank=rank, plan=plan, stage=stage, h=h_g, h_s=h_s, peers_g=peers_g, peers_s=peers_s,
+                         tail=(tail_lo is not None), rows=rows, h_r=h_r, peers_r=peers_r, rows_max=ROWS_MAX,
+                         ce_streams=[torch.cuda.Stream() for _ in range(3)])
         torch.cuda.synchronize()
-        dist.barrier(group=self.pg)
 
     def _peer_reduce(self, idx):
         """Steps 1-4 of _setup_peer for bucket `idx` on the current (side) stream."""
         pr = self.peer
         W, r = self.world, pr["rank"]
-        off, ln, sl, soff = pr["plan"][idx - 1]
+        off, ln, sl, soff = pr["plan"][idx - 1] if idx >= 1 else pr["plan"][-1]   # idx 0 = the embedding tail
 
         def sl_range(k):
             a = min(k * sl, ln)
@@ -199,6 +224,48 @@ class GradBuckets(object):
             torch.distributed.all_reduce(buf, group=self.pg)
         else:
             self.pending.append(torch.distributed.all_reduce(buf, group=self.pg, async_op=True))
+
+    def reduce_tail(self):
+        """Dense rest of the embedding bucket (position / type tables, LayerNorms, image embedder): cast to bf16
+        into the symmetric range and exchanged like a layer bucket, on the side stream."""
+        pr = self.peer
+        lo = self.g16_lo
+        hi = self.segments[0][1]
+        cur = torch.cuda.current_stream()
+        if self._cast_stream is None:
+            self._cast_stream = torch.cuda.Stream()
+        self._cast_stream.wait_stream(cur)
+        with torch.cuda.stream(self._cast_stream):
+            ops.cast_f32_to_bf16(self.grad[lo:hi], self.g16[0:hi - lo])
+            self._peer_reduce(0)
+        self._side_work = True
+
+    def allgather_rows(self, rows):
+        """All ranks' [n, H] bf16 row blocks -> [world * n, H] (rank-major), moved by the copy engines: every rank
+        copies its block into its slot of every peer's symmetric buffer (peer copies spread over helper streams so
+        several engines / NVLink paths run at once), then one barrier. None when the block does not fit."""
+        pr = self.peer
+        n, H = rows.shape
+        cnt = n * H
+        if pr is None or cnt > pr["rows_max"] or cnt % 8:
+            return None
+        W, r = self.world, pr["rank"]
+        cur = torch.cuda.current_stream()
+        src = rows.reshape(-1)
+        ev = cur.record_event()
+        streams = pr["ce_streams"]
+        for i, st in enumerate(streams):
+            st.wait_event(ev)
+        for d in range(1, W):
+            p = (r + d) % W
+            with torch.cuda.stream(streams[(d - 1) % len(streams)]):
+                pr["peers_r"][p][r * cnt:(r + 1) * cnt].copy_(src, non_blocking=True)
+        pr["rows"][r * cnt:(r + 1) * cnt].copy_(src, non_blocking=True)
+        for st in streams[:min(len(streams), W - 1)]:
+            cur.wait_stream(st)
+        rows.record_stream(cur)
+        pr["h_r"].barrier(channel=0)
+        return pr["rows"][:W * cnt].view(W * n, H)
 
     def join_side(self):
         """Order the current stream behind the side stream's bucket exchanges issued so far."""
@@ -277,11 +344,6 @@ class TrainStep(object):
         self._skip_detected = False
         self._build_runs()
 
-        # gradient buckets: index 0 = embeddings, 1.. = encoder layers (the last also holds pooler + head)
-        self.comm = GradBuckets([(e[0], e[2]) for e in store.entries], store.grad, process_group, self.world,
-                                comm_dtype=comm_dtype, comm_impl=comm_impl)
-        self.buckets = self.comm.segments
-        self.comm.sync = not overlap_comm
         # Word-embedding gradient [vocab, H] (20 % of all parameters, produced LAST by every backward, so its
         # dense all-reduce could not overlap anything, and row-sparse: <= B*T rows per micro-batch): with
         # world_size > 1 the micro-batches hand their touched rows over instead of scattering them, and after
@@ -291,6 +353,12 @@ class TrainStep(object):
         for name, p, off, cnt in store.entries:
             if name.endswith("embeddings.word_embeddings.weight"):
                 self.word_slice = (off, off + cnt, p)
+        # gradient buckets: index 0 = embeddings, 1.. = encoder layers (the last also holds pooler + head)
+        tail_lo = self.word_slice[1] if (self.word_slice is not None and self.word_slice[0] == 0 and overlap_comm) else None
+        self.comm = GradBuckets([(e[0], e[2]) for e in store.entries], store.grad, process_group, self.world,
+                                comm_dtype=comm_dtype, comm_impl=comm_impl, tail_lo=tail_lo)
+        self.buckets = self.comm.segments
+        self.comm.sync = not overlap_comm
         self.sparse_word = True
         self._word_rows = None
         self._word_dense = None
@@ -429,25 +497,42 @@ class TrainStep(object):
         rows = self._word_rows[0][0] if len(self._word_rows) == 1 else torch.cat([r for r, _, _ in self._word_rows], 0)
         self._word_rows = None
         n, H = rows.shape
-        all_rows = torch.empty(self.world * n, H, device=rows.device, dtype=rows.dtype)
+        rows = rows.contiguous()
+        peer_tail = self.comm.peer is not None and self.comm.peer["tail"]
+        if peer_tail:
+            # dense rest of the embedding bucket: bf16 two-shot exchange on the side stream, beside the row copies
+            self.comm.reduce_tail()
+            self.comm._tail_done = True
+        all_rows = self.comm.allgather_rows(rows) if self.comm.peer is not None else None
         layer_handles, self.comm.pending = self.comm.pending, []
-        gather = dist.all_gather_into_tensor(all_rows, rows.contiguous(), group=self.pg, async_op=True)
-        # the dense remainder of the embedding bucket (position / type tables, LayerNorms, image embedder)
-        # is reduced behind the row exchange, beside the segment add below
-        for a, b in ((b_lo, min(lo, b_hi)), (max(hi, b_lo), b_hi)):
-            if b > a:
-                self.comm.pending.append(dist.all_reduce(self.store.grad[a:b], group=self.pg, async_op=True))
-        # while those travel: squared norm of the (already reduced) encoder-layer range
+        gather = None
+        if all_rows is None:
+            all_rows = torch.empty(self.world * n, H, device=rows.device, dtype=rows.dtype)
+            gather = dist.all_gather_into_tensor(all_rows, rows, group=self.pg, async_op=True)
+        if not peer_tail:
+            # the dense remainder of the embedding bucket (position / type tables, LayerNorms, image embedder)
+            # is reduced behind the row exchange, beside the segment add below
+            for a, b in ((b_lo, min(lo, b_hi)), (max(hi, b_lo), b_hi)):
+                if b > a:
+                    self.comm.pending.append(dist.all_reduce(self.store.grad[a:b], group=self.pg, async_op=True))
+        # while those travel: squared norm of the (already reduced) bf16 range
         self._sumsq_layers_early(layer_handles)
-        gather.wait()
+        if gather is not None:
+            gather.wait()
         # identical (all_rows, ids) on every rank + a deterministic, atomic-free segment add (rows sorted by
         # id by the permutation computed at the window start, each run summed in order) => bit-identical
         # word-embedding gradients on all replicas
         cur.wait_event(self._ids_event)
         tot = self.world * n
         assert self._ids_sorted.numel() == tot, "word-row exchange: ids of the window do not match its rows"
+        # the table was zero before (the optimizer clears the gradients): the segment add also takes the table's
+        # share of the clipping norm from the rows it writes, so nobody reads the 89 MB table for it
+        fuse_norm = self._sumsq_done_from is not None and self._sumsq_done_from == hi and lo == 0
         ops._call("b200u_embedding_segment_add", P(all_rows), P(self._ids_sorted), P(self._ids_perm),
-                  P(self.store.grad[lo:hi]), tot, H, C.c_longlong(pad), C.c_longlong((hi - lo) // H))
+                  P(self.store.grad[lo:hi]), tot, H, C.c_longlong(pad), C.c_longlong((hi - lo) // H),
+                  P(self.sumsq) if fuse_norm else None)
+        if fuse_norm:
+            self._sumsq_done_from = 0
 
     def micro_step(self, batch, last, first=True):
         return self._backward(self._forward_loss(batch, last, first))
@@ -572,13 +657,20 @@ class TrainStep(object):
         g = self.store.grad
         n = g.numel()
         g16, lo16, hi16 = self.comm.bf16_range()
+        if self.comm.peer is not None and self.comm.peer["tail"]:
+            if not getattr(self.comm, "_tail_done", False):
+                # the embedding bucket travelled densely in fp32 this step: refresh its bf16 copy, which Adam reads
+                b_hi = self.buckets[0][1]
+                ops.cast_f32_to_bf16(g[lo16:b_hi], g16[0:b_hi - lo16])
+            self.comm._tail_done = False
         if self._sumsq_done_from is not None:
             # the layer range was summed early: add the embedding range [0, lo16) (fp32)
             if self._sumsq_on_side:
                 torch.cuda.current_stream().wait_stream(self._sumsq_stream)
                 self._sumsq_on_side = False
-            ops._call("b200u_grad_sumsq", P(g), C.c_size_t(self._sumsq_done_from), P(self.sumsq), None,
-                      C.c_size_t(0), C.c_size_t(0))
+            if self._sumsq_done_from > 0:
+                ops._call("b200u_grad_sumsq", P(g), C.c_size_t(self._sumsq_done_from), P(self.sumsq), None,
+                          C.c_size_t(0), C.c_size_t(0))
             self._sumsq_done_from = None
         else:
             self.sumsq.zero_()
