@@ -165,6 +165,12 @@ __device__ __forceinline__ uint32_t attn_rng(uint32_t key, uint32_t block_idx, i
     return i_odd ? lo : hi;
 }
 
+__device__ __forceinline__ unsigned long long globaltimer_ns() {   // device-wide nanosecond clock (bring-up stamps)
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
 // Programmatic dependent launch (see launch_k above). No-ops when launched without the attribute.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }

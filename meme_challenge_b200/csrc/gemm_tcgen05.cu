@@ -45,7 +45,7 @@ struct GemmArgs {
 
 #define DBG_STAMP(slot)                                                     \
     do {                                                                    \
-        if (g.dbg) g.dbg[(size_t)blockIdx.x * 8 + (slot)] = clock64();      \
+        if (g.dbg) g.dbg[(size_t)blockIdx.x * 8 + (slot)] = (g.dbg_mode == 3) ? (long long)globaltimer_ns() : clock64(); \
     } while (0)
 
 // ---------------------------------------------------------------------------------------
