@@ -225,11 +225,12 @@ int b200u_embedding_scatter_add(const void* d, const long long* ids, int ids_bat
 /* Deterministic (atomic-free) form for rows sorted by id: ids_sorted ascending, perm[p] = source row of
  * sorted entry p. One read-modify-write per distinct id, rows of a run added in sorted order, so equal
  * inputs give bit-identical tables (data-parallel exchange of the touched word-embedding rows).
- * sumsq (f64 [1] or NULL): += sum of squares of the rows written, i.e. the table's share of the gradient norm
- * when the table was zero before the call (the fused optimizer clears it every step). */
+ * sumsq (f64 [sumsq_slots] or NULL): slot (block % sumsq_slots) += sum of squares of the rows written; the slots'
+ * total is the table's share of the gradient norm when the table was zero before the call (the fused optimizer
+ * clears it every step). Several slots keep thousands of warps from serialising on one L2 address. */
 int b200u_embedding_segment_add(const void* d, const long long* ids_sorted, const long long* perm,
                                 float* table_grad, int n, int H, long long padding_idx, long long rows,
-                                double* sumsq, b200u_stream_t stream);
+                                double* sumsq, int sumsq_slots, b200u_stream_t stream);
 /* pos_linear weight gradient: dW[h,c] += sum_r dp[r,h] * pos7[r,c]. */
 int b200u_pos_linear_wgrad(const void* dp, const float* pos7, float* dW, int n, int H,
                            b200u_stream_t stream);

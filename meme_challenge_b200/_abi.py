@@ -39,7 +39,7 @@ SIGNATURES = {
     "b200u_txt_embed_fwd": (_i, [_p, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _f, _p, _p]),
     "b200u_img_embed_fwd": (_i, [_p] * 16 + [_i, _i, _i, _f, _p, _p]),
     "b200u_embedding_scatter_add": (_i, [_p, _p, _i, _i, _ll, _p, _i, _i, _ll, _ll, _p]),
-    "b200u_embedding_segment_add": (_i, [_p, _p, _p, _p, _i, _i, _ll, _ll, _p, _p]),
+    "b200u_embedding_segment_add": (_i, [_p, _p, _p, _p, _i, _i, _ll, _ll, _p, _i, _p]),
     "b200u_input_errors": (_i, [_p, _i]),
     "b200u_pos_linear_wgrad": (_i, [_p, _p, _p, _i, _i, _p]),
     "b200u_attention_fwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p, _p]),

@@ -323,7 +323,7 @@ __global__ void __launch_bounds__(256)
 embedding_segment_add_kernel(const bf16* __restrict__ d, const long long* __restrict__ ids_sorted,
                              const long long* __restrict__ perm, float* __restrict__ table_grad, int n,
                              int H, long long padding_idx, int nchunk, long long rows,
-                             unsigned* __restrict__ err, double* __restrict__ sumsq) {
+                             unsigned* __restrict__ err, double* __restrict__ sumsq, int sumsq_slots) {
     pdl_sync();
     const int lane = threadIdx.x & 31;
     const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -382,7 +382,8 @@ embedding_segment_add_kernel(const bf16* __restrict__ d, const long long* __rest
     }
     if (sumsq) {   // the table's share of the global gradient norm, valid when the table was zero before this launch
         sq = warp_sum(sq);
-        if (lane == 0) atomicAdd(sumsq, (double)sq);
+        // thousands of warps: spread over the caller's slots, same-address atomics would serialise in L2
+        if (lane == 0) atomicAdd(sumsq + (blockIdx.x % (unsigned)sumsq_slots), (double)sq);
     }
 }
 
@@ -517,15 +518,17 @@ extern "C" int b200u_embedding_scatter_add(const void* d, const long long* ids, 
 
 extern "C" int b200u_embedding_segment_add(const void* d, const long long* ids_sorted, const long long* perm,
                                            float* table_grad, int n, int H, long long padding_idx,
-                                           long long rows, double* sumsq, b200u_stream_t stream_) {
+                                           long long rows, double* sumsq, int sumsq_slots,
+                                           b200u_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     B200U_CHECK_ARG(d && ids_sorted && perm && table_grad, "embedding_segment_add: null pointer");
     B200U_CHECK_ARG(H % 8 == 0, "embedding_segment_add: H must be a multiple of 8");
+    B200U_CHECK_ARG(!sumsq || sumsq_slots >= 1, "embedding_segment_add: sumsq needs at least one slot");
     if (n == 0) return B200U_OK;
     const int nchunk = (H + 255) / 256;
     const long long warps = (long long)n * nchunk;
     launch_k(embedding_segment_add_kernel, dim3((unsigned)((warps + 7) / 8)), dim3(256), 0, stream, (const bf16*)d,
-             ids_sorted, perm, table_grad, n, H, padding_idx, nchunk, rows, dev_err_ptr(), sumsq);
+             ids_sorted, perm, table_grad, n, H, padding_idx, nchunk, rows, dev_err_ptr(), sumsq, sumsq_slots);
     B200U_CHECK_LAUNCH("embedding_segment_add_kernel");
     return B200U_OK;
 }

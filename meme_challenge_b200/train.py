@@ -313,6 +313,8 @@ class TrainStep(object):
         self._ids_stream = None
         self._ids_event = None
         self._sumsq_done_from = None
+        self._word_sq = None
+        self._ce_rows = os.environ.get("B200U_DP_ROWS", "1") != "0"
         self._sumsq_stream = None
         self._sumsq_on_side = False
         self.early_sumsq = os.environ.get("B200U_EARLY_SUMSQ", "1") != "0"
@@ -354,7 +356,11 @@ class TrainStep(object):
             if name.endswith("embeddings.word_embeddings.weight"):
                 self.word_slice = (off, off + cnt, p)
         # gradient buckets: index 0 = embeddings, 1.. = encoder layers (the last also holds pooler + head)
-        tail_lo = self.word_slice[1] if (self.word_slice is not None and self.word_slice[0] == 0 and overlap_comm) else None
+        tail_lo = self.word_slice[1] if (self.word_slice is not None and self.word_slice[0] == 0 and overlap_comm
+                                         and os.environ.get("B200U_DP_TAIL", "0") == "1") else None
+        # (B200U_DP_TAIL=1 also moves the dense rest of the embedding bucket onto the copy engines as one more bf16
+        #  bucket: measured -15 us on 2 GPUs but +70 us on 8, where its two extra barriers sit on the exposed tail, so
+        #  the fp32 NCCL all-reduce beside the row exchange stays the default)
         self.comm = GradBuckets([(e[0], e[2]) for e in store.entries], store.grad, process_group, self.world,
                                 comm_dtype=comm_dtype, comm_impl=comm_impl, tail_lo=tail_lo)
         self.buckets = self.comm.segments
@@ -503,7 +509,7 @@ class TrainStep(object):
             # dense rest of the embedding bucket: bf16 two-shot exchange on the side stream, beside the row copies
             self.comm.reduce_tail()
             self.comm._tail_done = True
-        all_rows = self.comm.allgather_rows(rows) if self.comm.peer is not None else None
+        all_rows = self.comm.allgather_rows(rows) if (self.comm.peer is not None and self._ce_rows) else None
         layer_handles, self.comm.pending = self.comm.pending, []
         gather = None
         if all_rows is None:
@@ -528,10 +534,15 @@ class TrainStep(object):
         # the table was zero before (the optimizer clears the gradients): the segment add also takes the table's
         # share of the clipping norm from the rows it writes, so nobody reads the 89 MB table for it
         fuse_norm = self._sumsq_done_from is not None and self._sumsq_done_from == hi and lo == 0
+        if fuse_norm:
+            if self._word_sq is None:
+                self._word_sq = torch.zeros(256, device=rows.device, dtype=torch.float64)
+            self._word_sq.zero_()
         ops._call("b200u_embedding_segment_add", P(all_rows), P(self._ids_sorted), P(self._ids_perm),
                   P(self.store.grad[lo:hi]), tot, H, C.c_longlong(pad), C.c_longlong((hi - lo) // H),
-                  P(self.sumsq) if fuse_norm else None)
+                  P(self._word_sq) if fuse_norm else None, 256)
         if fuse_norm:
+            self.sumsq.add_(self._word_sq.sum())
             self._sumsq_done_from = 0
 
     def micro_step(self, batch, last, first=True):
