@@ -745,11 +745,7 @@ static int launch_fwd(const void* qkv, const float* mask, void* ctx, float* lse,
                       int H, DropoutCfg dc, cudaStream_t stream) {
     const int LP = (L + 15) / 16 * 16;
     const size_t smem = (size_t)(2 * LP + TQ) * HD * 2 + (size_t)((L + 63) & ~63) * 4;
-    static size_t set_for = 0;
-    if (smem > set_for) {
-        B200U_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        set_for = smem;
-    }
+    if (int rc = ensure_dyn_smem((const void*)attn_fwd_kernel, smem)) return rc;
     launch_k(attn_fwd_kernel, dim3(dim3(B * nh, (L + TQ - 1) / TQ)), dim3(128), smem, stream, (const bf16*)qkv, mask, (bf16*)ctx, lse, L, LP, nh, H, dc);
     B200U_CHECK_LAUNCH("attn_fwd_kernel");
     return B200U_OK;
@@ -763,23 +759,12 @@ static int launch_bwd(const void* qkv, const float* mask, const void* ctx, const
     bf16* scrS = scrP + (size_t)B * nh * L * LP;
     const size_t smem1 = (size_t)(2 * LP + 2 * TQ) * HD * 2 + (size_t)(LP + 2 * TQ) * 4;
     const size_t smem2 = (size_t)4 * LP * HD * 2;
-    static size_t set1 = 0, set2 = 0;
-    if (smem1 > set1) {
-        B200U_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
-        set1 = smem1;
-    }
-    if (smem2 > set2) {
-        B200U_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-        set2 = smem2;
-    }
+    if (int rc = ensure_dyn_smem((const void*)attn_bwd_dq_kernel, smem1)) return rc;
+    if (int rc = ensure_dyn_smem((const void*)attn_bwd_dkv_kernel, smem2)) return rc;
     if (LP <= FUSED_MAX_LP) {
         // one CTA per (sample, head): Q, K, V, dO (4 tiles), Pd and dS (3 tiles each) + mask / lse / D
         const size_t smem = (size_t)10 * LP * HD * 2 + (size_t)(192 + 2 * LP) * 4;
-        static size_t set3 = 0;
-        if (smem > set3) {
-            B200U_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            set3 = smem;
-        }
+        if (int rc = ensure_dyn_smem((const void*)attn_bwd_fused_kernel, smem)) return rc;
         launch_k(attn_bwd_fused_kernel, dim3(B * nh), dim3(LP * 2), smem, stream, (const bf16*)qkv, mask, (const bf16*)ctx, (const bf16*)dctx, lse, (bf16*)dqkv, dbias, L, LP, nh, H, dc);
         B200U_CHECK_LAUNCH("attn_bwd_fused_kernel");
         return B200U_OK;

@@ -55,6 +55,7 @@ void count_launch();  // bumps the kernel-launch counter read by b200u_launch_co
 bool prof_begin(cudaStream_t st, double flops, int* slot);
 void prof_end(cudaStream_t st, int slot);
 int num_sms();  // cached cudaDevAttrMultiProcessorCount of the current device
+int ensure_dyn_smem(const void* kern, size_t bytes);  // per-device, thread-safe MaxDynamicSharedMemorySize >= bytes
 unsigned* dev_err_ptr();  // per-device input-error word (b200u_input_errors), bits below
 enum { ERR_WORD_ID = 1, ERR_POS_ID = 2, ERR_TYPE_ID = 4, ERR_GATHER_INDEX = 8, ERR_SCATTER_ID = 16 };
 bool pdl_enabled();  // b200u_set_pdl(): launch kernels with programmatic stream serialization

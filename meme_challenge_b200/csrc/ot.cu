@@ -228,11 +228,7 @@ extern "C" int b200u_ipot(const float* cost, const unsigned char* x_pad, const u
     const int Mp = M | 1;  // odd row stride: conflict-free column walks
     const size_t smem = ((size_t)2 * N * Mp + M + N) * sizeof(float);
     B200U_CHECK_ARG(smem <= 220 * 1024, "ipot: %d x %d plan does not fit in shared memory", N, M);
-    static size_t set_for = 0;
-    if (smem > set_for) {
-        B200U_CHECK_CUDA(cudaFuncSetAttribute(ipot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        set_for = smem;
-    }
+    if (int rc = ensure_dyn_smem((const void*)ipot_kernel, smem)) return rc;
     launch_k(ipot_kernel, dim3(B), dim3(256), smem, stream, cost, x_pad, y_pad, T, M, N, Mp, beta, iterations, k);
     B200U_CHECK_LAUNCH("ipot");
     return B200U_OK;

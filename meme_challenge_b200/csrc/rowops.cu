@@ -468,14 +468,10 @@ extern "C" int b200u_layernorm_bwd(const void* dy, const void* x, int x_dtype, c
     const int rows_per_cta = (M + grid - 1) / grid;
     grid = (M + rows_per_cta - 1) / rows_per_cta;
     const size_t smem = (size_t)3 * rows_per_pass * H * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
-        B200U_CHECK_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<bf16, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        B200U_CHECK_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<bf16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        B200U_CHECK_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<float, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        B200U_CHECK_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<float, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
-    }
+    if (int rc = ensure_dyn_smem((const void*)layernorm_bwd_kernel<bf16, 3>, 200 * 1024)) return rc;
+    if (int rc = ensure_dyn_smem((const void*)layernorm_bwd_kernel<bf16, 4>, 200 * 1024)) return rc;
+    if (int rc = ensure_dyn_smem((const void*)layernorm_bwd_kernel<float, 3>, 200 * 1024)) return rc;
+    if (int rc = ensure_dyn_smem((const void*)layernorm_bwd_kernel<float, 4>, 200 * 1024)) return rc;
     const bool narrow = H <= 768;
 #define LNB_LAUNCH(TX, NV) \
     launch_k(layernorm_bwd_kernel<TX, NV>, dim3(grid), dim3(LNB_THREADS), smem, stream, (const bf16*)dy, (const TX*)x, mean, rstd, gamma, (bf16*)dx, (bf16*)dz, dgamma, dbeta, dbias, M, H, rows_per_cta, rows_per_pass, dc, drop_on_input)

@@ -2,7 +2,9 @@
 #include "../../include/b200u.h"
 #include "common.cuh"
 
+#include <map>
 #include <mutex>
+#include <utility>
 
 #include <cudaTypedefs.h>
 #include <stdarg.h>
@@ -114,6 +116,22 @@ int make_tmap_3d(CUtensorMap* tm, const void* ptr, int batch, int rows, int cols
         set_error("cuTensorMapEncodeTiled(3d) failed (%d) ptr=%p batch=%d rows=%d cols=%d ld=%d box_rows=%d", (int)r,
                   ptr, batch, rows, cols, ld, box_rows);
         return B200U_ERR_CUDA;
+    }
+    return B200U_OK;
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per device and PyTorch calls the library from its main and autograd
+// threads: remember, per (device, kernel), the largest size already granted, under one mutex.
+static std::mutex g_smem_mu;
+static std::map<std::pair<int, const void*>, size_t> g_smem_set;
+int ensure_dyn_smem(const void* kern, size_t bytes) {
+    int dev = 0;
+    B200U_CHECK_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(g_smem_mu);
+    size_t& have = g_smem_set[std::make_pair(dev, kern)];
+    if (bytes > have) {
+        B200U_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        have = bytes;
     }
     return B200U_OK;
 }

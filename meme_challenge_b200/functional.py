@@ -200,6 +200,10 @@ class BertLayerFn(torch.autograd.Function):
     def backward(ctx, dx2):
         (x0,) = ctx.saved_tensors
         p, rt = ctx.p, ctx.rt
+        if ctx.keep is None:
+            # the saved activations (raw device pointers inside ctx.saved) are released after the first backward
+            raise _lib.B200UError("BertLayer backward was already run for this forward (retain_graph / a second "
+                                  "backward is not supported: the saved activations are freed after the first one)")
         dx2 = dx2.contiguous()
         g = _layer_grads(ctx.layer, rt.store)
         w = _scratch(p.B * p.L, p.H, p.I, x0.device, p.B, p.L, p.heads)

@@ -29,15 +29,39 @@ def _cost_fwd(x, y, x_pad, y_pad, eps):
     return cost, xinv, yinv
 
 
+class _CosineCost(torch.autograd.Function):
+    """cosine distance with its gradient: the backward kernel of the OT distance takes the upstream weights of the
+    cost entries as a [B, N, M] matrix (there the transport plan), here d loss / d cost transposed."""
+
+    @staticmethod
+    def forward(ctx, x, y, eps):
+        xf = x.detach().float().contiguous()
+        yf = y.detach().float().contiguous()
+        cost, xinv, yinv = _cost_fwd(xf, yf, None, None, eps)
+        ctx.save_for_backward(xf, yf, xinv, yinv)
+        ctx.in_dtypes = (x.dtype, y.dtype)
+        return cost
+
+    @staticmethod
+    def backward(ctx, dcost):
+        x, y, xinv, yinv = ctx.saved_tensors
+        B, M, D = x.shape
+        N = y.shape[1]
+        w = dcost.float().transpose(1, 2).contiguous()
+        one = torch.ones(B, device=x.device, dtype=torch.float32)
+        dx = torch.empty_like(x)
+        dy = torch.empty_like(y)
+        ops._call("b200u_cosine_cost_bwd", P(x), P(y), P(xinv), P(yinv), None, None, P(w), P(one), P(dx), P(dy),
+                  B, M, N, D)
+        return dx.to(ctx.in_dtypes[0]), dy.to(ctx.in_dtypes[1]), None
+
+
 def cost_matrix_cosine(x, y, eps=1e-5):
-    """[B, L_x, D] [B, L_y, D] -> [B, Lx, Ly] cosine distance (ot.py:11-21). Forward only; use
-    optimal_transport_dist for the differentiable path."""
+    """[B, L_x, D] [B, L_y, D] -> [B, Lx, Ly] cosine distance (ot.py:11-21), differentiable like the reference's."""
     assert x.dim() == y.dim()
     assert x.size(0) == y.size(0)
     assert x.size(2) == y.size(2)
-    x = x.detach().float().contiguous()
-    y = y.detach().float().contiguous()
-    return _cost_fwd(x, y, None, None, eps)[0]
+    return _CosineCost.apply(x, y, eps)
 
 
 def trace(x):

@@ -561,6 +561,18 @@ def test_training_mode_dropout_runs_and_differs():
     assert g is not None and torch.isfinite(g).all() and g.abs().max() > 0
 
 
+def test_second_backward_through_released_activations_raises():
+    """The layer's saved activations are raw device buffers released after the first backward: a second backward
+    (retain_graph=True) must fail loudly instead of reading freed memory."""
+    _require_gpu()
+    m = _build(TINY, IMG_DIM).eval()
+    b = O.synth_batch(2, 12, 10, seed=3, img_dim=IMG_DIM, vocab=TINY["vocab_size"], min_txt=2, min_bb=2)
+    out = m(**_kw(b)).sum()
+    out.backward(retain_graph=True)
+    with pytest.raises(Exception, match="already run"):
+        out.backward()
+
+
 def test_grad_accumulation_and_zero_grad_set_to_none():
     """Two backward passes accumulate like the reference's `elif grad_step: loss.backward()`
     (train_template.py:108-109); zero_grad(set_to_none=True) is survived."""
@@ -959,6 +971,24 @@ def test_ot_against_reference_golden(golden_dir):
     cm = cost.masked_fill(joint, 0)
     T2 = ot.ipot(cm, (6 - txt_pad.sum(1)).float(), txt_pad, (9 - img_pad.sum(1)).float(), img_pad, joint, 0.5, 50, 1)
     assert (T2.cpu() - Tref).norm() / Tref.norm() <= 1e-3
+
+
+def test_cost_matrix_cosine_is_differentiable():
+    """model/ot.py:11-21 is plain differentiable torch in the reference; here forward and backward are kernels."""
+    _require_gpu()
+    from meme_challenge_b200.model import ot
+    torch.manual_seed(2)
+    x = torch.randn(3, 12, 64, device=DEV, requires_grad=True)
+    y = torch.randn(3, 10, 64, device=DEV, requires_grad=True)
+    w = torch.randn(3, 12, 10, device=DEV)
+    (ot.cost_matrix_cosine(x, y) * w).sum().backward()
+    xr = x.detach().clone().requires_grad_(True)
+    yr = y.detach().clone().requires_grad_(True)
+    ref = 1 - torch.nn.functional.normalize(xr, p=2, dim=-1, eps=1e-5) @ torch.nn.functional.normalize(yr, p=2, dim=-1, eps=1e-5).transpose(1, 2)
+    (ref * w).sum().backward()
+    assert torch.allclose(ot.cost_matrix_cosine(x, y).detach(), ref.detach(), atol=1e-5)
+    assert torch.allclose(x.grad, xr.grad, rtol=1e-3, atol=1e-5)
+    assert torch.allclose(y.grad, yr.grad, rtol=1e-3, atol=1e-5)
 
 
 def test_ot_c5_shape_and_gradient_against_oracle():
