@@ -448,6 +448,65 @@ def _measure_pretrain(args, model_cfg, rank, world, dev, host, devb, L_):
                 launches_per_step=int(launches_per_step), n_params=n_params)
 
 
+def _measure_variants(args, model_cfg, dev):
+    """SURVEY.md 8(d), C2 side measurements on one GPU (fused window, CUDA graphs, inputs resident):
+    fwd+bwd only (no optimizer; the gradients are cleared instead) and the variable-length variant
+    (txt_len ~ U{8..64}, 36-100 regions per meme: every batch set has its own padded widths and its own graph)."""
+    from meme_challenge_b200.data.synthetic import synth_batch
+    from meme_challenge_b200.model.meme_uniter import MemeUniter
+    from meme_challenge_b200.model.model import UniterConfig, UniterModel
+    from meme_challenge_b200.train import TrainStep
+
+    def time_steps(run, n):
+        for i in range(args.warmup):
+            run(i)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n):
+            run(i)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    def dev_batch(seed, variable):
+        b = synth_batch(B, T, R, seed=seed, variable=variable)
+        d = {k: v.to(dev) for k, v in b.items() if torch.is_tensor(v)}
+        d["labels"] = d["labels"].float()
+        return d
+
+    out = {}
+    torch.manual_seed(0)
+    model = MemeUniter(UniterModel(UniterConfig.from_dict(model_cfg), 2048), model_cfg["hidden_size"], 1).to(dev).train()
+    ts = TrainStep(model, lr=3e-5, weight_decay=1e-3, gradient_accumulation=ACCUM, max_grad_norm=5.0, pos_wt=1.8,
+                   fuse_window=True)
+    steps = max(10, args.steps // 2)
+    # (a) forward + backward only
+    ts.capture([dev_batch(1234 + i, False) for i in range(ACCUM)], warmup=2, optimizer=False)
+    ms = time_steps(lambda i: ts.replay(), steps)
+    out["fwd_bwd_only"] = {"value": round(ACCUM * B / (ms * 1e-3), 1), "ms_per_step": round(ms, 3),
+                           "what": "2 x 16 memes forward + backward, gradients cleared, no clip / Adam"}
+    # (b) variable-length batches, full optimizer step, one graph per batch set
+    graphs, widths = [], []
+    for k in range(4):
+        bs = [dev_batch(5000 + ACCUM * k + i, True) for i in range(ACCUM)]
+        ts.capture(bs, warmup=1)
+        graphs.append((ts._graph, ts._static, ts._static_cat, ts._static_out))
+        widths.append(max(int(b["attn_mask"].shape[1]) for b in bs))
+
+    def run_var(i):
+        ts._graph, ts._static, ts._static_cat, ts._static_out = graphs[i % len(graphs)]
+        ts.replay()
+    ms = time_steps(run_var, steps)
+    out["variable_length"] = {"value": round(ACCUM * B / (ms * 1e-3), 1), "ms_per_step": round(ms, 3),
+                              "what": "full optimizer step on ragged batches (txt_len ~ U{8..64}, 36-100 regions per meme; "
+                                      "padded joint widths of the 4 batch sets: %s)" % widths}
+    ts._graph = None
+    del graphs, ts, model
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_b200(args, rank, world, local_rank):
     import torch.distributed as dist
     from meme_challenge_b200 import _lib, roofline
@@ -469,6 +528,7 @@ def run_b200(args, rank, world, local_rank):
     torch.cuda.synchronize()
 
     other = None
+    variants = None
     if pretrain:
         main = _measure_pretrain(args, model_cfg, rank, world, dev, host, devb, L_)
         memes_per_step = B * world
@@ -484,6 +544,11 @@ def run_b200(args, rank, world, local_rank):
                          "e2e": round(args.steps * memes_per_step / (o["ms_e2e"] * 1e-3), 1)}
             except Exception as e:  # noqa: BLE001
                 sys.stderr.write("secondary window measurement failed: %s\n" % str(e)[:300])
+            if args.config == "base":
+                try:
+                    variants = _measure_variants(args, model_cfg, dev)
+                except Exception as e:  # noqa: BLE001
+                    sys.stderr.write("variant measurements failed: %s\n" % str(e)[:300])
 
     # ---- roofline legs (rank 0, no collectives)
     roof = None
@@ -554,6 +619,8 @@ def run_b200(args, rank, world, local_rank):
                 "clocks": main["clocks"], "roofline": roof}
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if variants is not None:
+            line["variants"] = variants
         _emit(line)
     if world > 1:
         # leave through os._exit so a communicator teardown that blocks cannot hang the launcher

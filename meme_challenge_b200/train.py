@@ -737,9 +737,10 @@ class TrainStep(object):
         self.lr_t.fill_(lr)
 
     # ------------------------------------------------------------------ public: one optimizer step
-    def step(self, batches):
+    def step(self, batches, optimizer=True):
         """batches: list of `gradient_accumulation` device batch dicts. Returns the list of
-        (loss[1], probs[B]) device tensors of the micro-batches.
+        (loss[1], probs[B]) device tensors of the micro-batches. optimizer=False (single replica, measurement):
+        forward + backward of the window only, then the gradients are cleared.
 
         The micro-batches of one accumulation window are independent until their gradients meet in the
         flat buffer, so the window is software-pipelined over two streams: the forward of micro-batch
@@ -786,12 +787,20 @@ class TrainStep(object):
                 ev_b = bwd(i, ev_b)
                 ev_f = ev_next
             main.wait_event(ev_b)     # join before the optimizer (and before the caller reads the outputs)
-        self.optimizer_step()
+        if optimizer:
+            self.optimizer_step()
+        else:
+            assert self.world == 1, "optimizer=False is a single-replica measurement mode"
+            if self._sumsq_on_side:
+                torch.cuda.current_stream().wait_stream(self._sumsq_stream)
+                self._sumsq_on_side = False
+            self._sumsq_done_from = None
+            self.store.grad.zero_()
         self.host_step += 1
         return outs
 
     # ------------------------------------------------------------------ CUDA-graph replay
-    def capture(self, example_batches, warmup=3):
+    def capture(self, example_batches, warmup=3, optimizer=True):
         """Capture one full optimizer step (all micro-batches + optimizer) in a CUDA graph over
         static input buffers. Returns the static buffers; fill them and call replay().
 
@@ -818,7 +827,7 @@ class TrainStep(object):
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
             for _ in range(warmup):
-                self.step(static)
+                self.step(static, optimizer=optimizer)
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         mode = "thread_local" if self.world > 1 else "global"
@@ -829,13 +838,13 @@ class TrainStep(object):
             hs = self.host_step
             dry = torch.cuda.CUDAGraph()
             with torch.cuda.graph(dry, capture_error_mode=mode):
-                self.step(static)
+                self.step(static, optimizer=optimizer)
             del dry
             self.host_step = hs
             self._detect_untouched()
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph, capture_error_mode=mode):
-            outs = self.step(static)
+            outs = self.step(static, optimizer=optimizer)
         self._graph, self._static, self._static_out = graph, static, outs
         return static
 
