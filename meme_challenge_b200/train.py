@@ -104,6 +104,23 @@ class GradBuckets(object):
                 self.g16 = torch.zeros(n - self.g16_lo, device=flat_grad.device, dtype=torch.bfloat16)
 
     # ------------------------------------------------------------------ copy-engine all-reduce over NVLink
+    @staticmethod
+    def slice_plan(segments, world, n_total, tail_lo=None):
+        """Layout of the copy-engine exchange: (first element of the bf16 range, its length, per-bucket
+        (offset in the bf16 range, bucket length, slice length, staging offset) for the encoder-layer buckets [+ the
+        dense tail of the embedding bucket as the LAST entry], staging elements). Rank r owns elements
+        [r * slice, (r + 1) * slice) of a bucket (clipped to its length); slice lengths are multiples of 8 elements
+        so every copy starts 16-byte aligned; a bucket's staging area holds one slice per source rank."""
+        g16_lo = segments[1][0] if tail_lo is None else tail_lo
+        ranges = list(segments[1:]) + ([(tail_lo, segments[0][1])] if tail_lo is not None else [])
+        plan, stage_off = [], 0
+        for (lo, hi) in ranges:
+            ln = hi - lo
+            sl = ((ln + world - 1) // world + 7) // 8 * 8
+            plan.append((lo - g16_lo, ln, sl, stage_off))
+            stage_off += world * sl
+        return g16_lo, n_total - g16_lo, plan, stage_off
+
     def _setup_peer(self, n_total, tail_lo=None):
         """Two-shot all-reduce of the bf16 layer buckets WITHOUT collective kernels on the SMs.
 
@@ -125,17 +142,7 @@ class GradBuckets(object):
         rank = dist.get_rank(self.pg)
         assert W - 1 <= 15, "b200u_slice_sum_bf16 takes at most 15 peers"
         group = self.pg if self.pg is not None else dist.group.WORLD
-        g16_lo = self.segments[1][0] if tail_lo is None else tail_lo
-        n16 = n_total - g16_lo
-        # per bucket: slice length (multiple of 8 elements = 16 bytes) and staging offset; the optional last plan
-        # entry is the dense tail of the embedding bucket
-        ranges = list(self.segments[1:]) + ([(tail_lo, self.segments[0][1])] if tail_lo is not None else [])
-        plan, stage_off = [], 0
-        for (lo, hi) in ranges:
-            ln = hi - lo
-            sl = ((ln + W - 1) // W + 7) // 8 * 8
-            plan.append((lo - g16_lo, ln, sl, stage_off))
-            stage_off += W * sl
+        g16_lo, n16, plan, stage_off = self.slice_plan(self.segments, W, n_total, tail_lo)
         g16 = symm_mem.empty(n16, dtype=torch.bfloat16, device=dev)
         stage = symm_mem.empty(max(stage_off, 8), dtype=torch.bfloat16, device=dev)
         g16.zero_()

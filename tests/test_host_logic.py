@@ -202,3 +202,32 @@ def test_reference_loader_runs_the_unmodified_reference():
                 img_pos_feat=b["img_pos_feat"], attention_mask=b["attn_mask"], gather_index=b["gather_index"],
                 output_all_encoded_layers=False)
     assert out.shape == (2, 1) and torch.isfinite(out).all()
+
+
+def test_copy_engine_exchange_slice_plan_covers_every_bucket():
+    """GradBuckets.slice_plan (train.py): the per-rank slices of every bucket tile it exactly, start 16-byte aligned,
+    and the staging areas of different (bucket, source rank) pairs never overlap -- for any world size, with and
+    without the dense embedding tail as an extra bucket."""
+    from meme_challenge_b200.train import GradBuckets
+    segments = [(0, 1000), (1000, 8088), (8088, 15176), (15176, 15176 + 7096)]   # embeddings + 3 "layers"
+    n = segments[-1][1]
+    for world in (2, 3, 4, 8, 16):
+        for tail_lo in (None, 200):
+            g16_lo, n16, plan, stage = GradBuckets.slice_plan(segments, world, n, tail_lo)
+            assert g16_lo == (segments[1][0] if tail_lo is None else tail_lo) and n16 == n - g16_lo
+            assert len(plan) == len(segments) - 1 + (tail_lo is not None)
+            used = []
+            for off, ln, sl, soff in plan:
+                assert sl % 8 == 0 and sl * world >= ln and off % 8 == 0 and soff % 8 == 0
+                covered = 0
+                for r in range(world):
+                    a = min(r * sl, ln)
+                    b = min(a + sl, ln)
+                    assert a % 8 == 0 or a == ln
+                    covered += b - a
+                assert covered == ln
+                used.append((soff, soff + world * sl))
+            used.sort()
+            assert all(used[i][1] <= used[i + 1][0] for i in range(len(used) - 1)) and used[-1][1] == stage
+            if tail_lo is not None:   # the tail bucket is the last plan entry and the first elements of the bf16 range
+                assert plan[-1][0] == 0 and plan[-1][1] == segments[0][1] - tail_lo
