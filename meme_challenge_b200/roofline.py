@@ -127,6 +127,33 @@ def hbm_kernels(dev, B, T, R, L, H, heads, n_params, hbm_gbs):
     dbq = torch.zeros(3 * H, device=dev)
     rec("attention_bwd", _time_graph(lambda i: ops.attention_bwd(qkv[i], mask, ctx, dctx, lse, B, L, heads, H, drop=d,
                                                                  dbias_qkv=dbq)), 9 * M * H * 2)
+    # K0 text embeddings: word + position rows in (fp32 tables), LayerNorm'd bf16 row out (+ the type row, negligible);
+    # SURVEY 8(d) counts 3 reads + 1 write of T*H bf16 = 0.39 MB per meme
+    import ctypes as C
+    P = _lib.ptr
+    V, PMAX = 28996, 512
+    word = torch.randn(V, H, device=dev) * 0.02
+    post = torch.randn(PMAX, H, device=dev) * 0.02
+    typ = torch.randn(2, H, device=dev) * 0.02
+    ids = [torch.randint(1000, V, (B, T), device=dev) for _ in range(2)]
+    pos_ids = torch.arange(T, device=dev).unsqueeze(0).repeat(B, 1).contiguous()
+    t_out = torch.empty(B * T, H, device=dev, dtype=torch.bfloat16)
+    t_sum = torch.empty(B * T, H, device=dev)
+    t_mean, t_rstd = torch.empty(B * T, device=dev), torch.empty(B * T, device=dev)
+    rec("txt_embed_fwd", _time_graph(lambda i: ops._call(
+        "b200u_txt_embed_fwd", P(ids[i]), P(pos_ids), T, None, P(word), P(post), P(typ), P(gam), P(bet), P(t_out),
+        P(t_sum), P(t_mean), P(t_rstd), B, T, H, V, PMAX, 2, 1e-12, C.byref(d))), 4 * B * T * H * 2)
+    # K2 image embeddings after img_linear: fp32 projection row + 7-d box in, LayerNorm'd bf16 row out
+    n_img = B * R
+    a_in = [torch.randn(n_img, H, device=dev) for _ in range(2)]
+    pos7 = torch.rand(n_img, 7, device=dev)
+    Wp, bp = torch.randn(H, 7, device=dev) * 0.1, torch.zeros(H, device=dev)
+    i_out = torch.empty(n_img, H, device=dev, dtype=torch.bfloat16)
+    i_p, i_s = torch.empty(n_img, H, device=dev), torch.empty(n_img, H, device=dev)
+    i_stats = torch.empty(6, n_img, device=dev)
+    rec("img_embed_fwd", _time_graph(lambda i: ops._call(
+        "b200u_img_embed_fwd", P(a_in[i]), P(pos7), P(Wp), P(bp), None, P(typ), P(gam), P(bet), P(gam), P(bet), P(gam),
+        P(bet), P(i_out), P(i_p), P(i_s), P(i_stats), n_img, H, 2, 1e-12, C.byref(d))), n_img * (H * 6 + 28))
     # gather_index concat: read txt + img rows once, write the joint sequence
     txt = [torch.randn(B, T, H, device=dev).bfloat16() for _ in range(2)]
     img = [torch.randn(B, R, H, device=dev).bfloat16() for _ in range(2)]
@@ -142,8 +169,6 @@ def hbm_kernels(dev, B, T, R, L, H, heads, n_params, hbm_gbs):
     chunk_run = torch.zeros(n // 1024, device=dev, dtype=torch.int32)
     coef, lr = torch.ones(1, device=dev), torch.tensor([3e-5], device=dev)
     step = torch.ones(1, device=dev, dtype=torch.int64)
-    import ctypes as C
-    P = _lib.ptr
     rec("adam_step", _time_graph(lambda i: ops._call("b200u_adam_step", P(p), P(g), P(m_), P(v), P(sh), C.c_size_t(n),
                                                      P(run_start), P(run_wd), P(chunk_run), 1, P(coef), P(lr), P(step),
                                                      0.9, 0.999, 1e-8, 1, None, C.c_size_t(0), C.c_size_t(0)), reps=4),
